@@ -1,0 +1,134 @@
+/*
+ * hdp_b200.h - C ABI of libhdp_b200.so: the two HDP hot paths on B200 (sm_100a).
+ *
+ * HDP (AgentOxygen/HDP v1.0.2) is pure Python + Numba and has no FFI of its own; the seams this
+ * library replaces are the two array-level kernels directly under its public functions, plus the
+ * per-block sweeps around them.  "reference" file:line below are relative to the HDP source tree.
+ *
+ *   hdp_b200_thresholds   replaces  compute_percentiles gufunc            hdp/threshold.py:52-78
+ *                                   + compute_percentiles_wrapper          hdp/threshold.py:81-93
+ *                                   (np.quantile as compiled by Numba:     numba/np/arraymath.py:1655-1704, 1754-1768)
+ *   hdp_b200_metrics      replaces  compute_heatwave_metrics              hdp/metric.py:304-341
+ *                                   (indicate_hot_days :280-301, index_heatwaves :11-60,
+ *                                    heatwave_frequency/number/duration/average :63-172)
+ *                                   + compute_heatwave_metrics_wrapper     hdp/metric.py:344-369
+ *   hdp_b200_hot_days     replaces  indicate_hot_days                     hdp/metric.py:280-301   (parity checks)
+ *   *_host variants       the same calls with HOST buffers (chunked H2D -> kernels -> D2H inside).
+ *
+ * Conventions
+ *   - Pointers named d_*  are DEVICE pointers owned by the caller (e.g. torch tensors).
+ *   - Pointers named h_*  are HOST pointers to small index tables (KBs); they are copied inside the call
+ *     and may be freed as soon as the call returns.
+ *   - Every device call takes a cudaStream_t (as void*), enqueues its work on it and returns without
+ *     synchronising the device (small pageable-host table uploads are the only host-blocking step).
+ *   - No allocation inside the device calls: scratch comes from the caller-sized workspace
+ *     (hdp_b200_*_workspace_bytes).  The *_host variants allocate and free their own device buffers.
+ *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = one of the HDP_B200_ERR_* codes.  Nothing throws.
+ *   - Element (t, c) of a measure array lives at base[t*ld_t + c*ld_c] (strides in ELEMENTS).
+ *     The fast path is time-major, cell-contiguous (ld_c == 1); any other layout is first
+ *     normalised into the workspace by a transposing copy.
+ *   - Thread-compatible: concurrent calls must use different workspaces.
+ */
+#ifndef HDP_B200_H
+#define HDP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDP_B200_ABI_VERSION 1
+
+#define HDP_B200_OK                 0
+#define HDP_B200_ERR_INVALID       (-1)  /* null pointer, negative size, quantile outside [0,1] or NaN, bad table entry */
+#define HDP_B200_ERR_UNSUPPORTED   (-2)  /* shape outside what the kernels support (see hdp_b200_strerror) */
+#define HDP_B200_ERR_WORKSPACE     (-3)  /* workspace pointer null or smaller than *_workspace_bytes() */
+#define HDP_B200_ERR_NO_DEVICE     (-4)  /* no CUDA device / not an sm_100 device */
+#define HDP_B200_ERR_NOMEM         (-5)  /* host-side allocation failed */
+
+#define HDP_B200_MAX_PERCENTILES   32
+#define HDP_B200_MAX_DEFINITIONS   32
+#define HDP_B200_MAX_WINDOW        32768 /* samples pooled per day-of-year window (W * n_y) */
+
+int         hdp_b200_abi_version(void);
+const char *hdp_b200_strerror(int code);
+/* SM count and compute capability of the current device; HDP_B200_ERR_NO_DEVICE if there is none. */
+int         hdp_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Path 1 - thresholds.   reference: hdp/threshold.py:52-93
+ *
+ *   d_temps       f32 baseline series, element (t, c) at [t*ld_t + c*ld_c], t < T_b, c < C
+ *   h_time_index  i32 [n_doy, n_y]  time indices of each day-of-year row, -1 padded (threshold.py:28-39);
+ *                 negative entries index from the end of the series like the reference's gufunc does
+ *   h_win_rows    i32 [n_doy, W]    rows of time_index pooled by the window of each row (threshold.py:41-48);
+ *                 window_samples[d] == time_index[win_rows[d]].ravel() is the reference's table
+ *   h_q           f64 [P]           quantiles in [0, 1]
+ *   d_out         f64 [C, n_doy, P] (the reference's (<cells>, doy, percentile) order)
+ * ------------------------------------------------------------------------------------------------- */
+size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                                           int n_doy, int n_y, int W, int P);
+
+int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                        const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
+                        const double *h_q, int P,
+                        double *d_out,
+                        void *d_workspace, size_t workspace_bytes, void *stream);
+
+int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                             const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
+                             const double *h_q, int P,
+                             double *h_out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Path 2 - heatwave metrics.   reference: hdp/metric.py:11-172, 280-369
+ *
+ *   d_measure     f32 series, element (t, c) at [t*ld_t + c*ld_c], t < T, c < C
+ *   d_thr         f64 [C, n_doy, P]   thresholds, exactly what path 1 writes
+ *   h_doy_map     i32 [T]             day-of-year row of every time step (metric.py:265-277), 0 <= v < n_doy
+ *   h_defs        i32 [D, 3]          [min_duration, max_break, max_subs] per definition (metric.py:11)
+ *   h_season_north / h_season_south   i32 [Y, 2] season [start, end) time indices per hemisphere
+ *                 (metric.py:175-262); Python slice semantics are applied to negative / out-of-range values
+ *   d_is_south    u8 [C] 1 = use the southern table (lat < 0, metric.py:247-252); NULL = all northern
+ *   d_out         u16 [4, P, D, Y, C]  metric-major: HWF, HWN, HWD, HWA (= HWF / HWN truncated, metric.py:336-340);
+ *                 the reference's int64 (percentile, definition, <cells>, metric, year) array is
+ *                 out[m][p][d][y][c] widened.  Every value is <= the longest season, which must be < 65536.
+ * ------------------------------------------------------------------------------------------------- */
+size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                                        int n_doy, int P, int D, int Y);
+
+int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                     const double *d_thr, int n_doy, int P,
+                     const int32_t *h_doy_map,
+                     const int32_t *h_defs, int D,
+                     const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                     const uint8_t *d_is_south,
+                     uint16_t *d_out,
+                     void *d_workspace, size_t workspace_bytes, void *stream);
+
+int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                          const double *h_thr, int n_doy, int P,
+                          const int32_t *h_doy_map,
+                          const int32_t *h_defs, int D,
+                          const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                          const uint8_t *h_is_south,
+                          uint16_t *h_out);
+
+/* Hot-day mask only (parity checks): d_mask u8 [P, T, C], 1 where measure > threshold[doy_map[t]]
+ * compared in double precision, NaN -> 0 (metric.py:280-301).  Same workspace size as hdp_b200_metrics. */
+int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                      const double *d_thr, int n_doy, int P,
+                      const int32_t *h_doy_map,
+                      uint8_t *d_mask,
+                      void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Last kernel-launch counters (for bench.py's gpu_launches claim): number of kernels this library has
+ * launched since it was loaded. */
+int64_t hdp_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDP_B200_H */

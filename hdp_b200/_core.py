@@ -1,0 +1,233 @@
+"""Array-level API over the C ABI: torch CUDA tensors (device memory + streams) in, tensors out.
+
+These are the two seams of the reference that the CUDA library replaces:
+
+* :func:`thresholds_array`  <- ``compute_percentiles`` gufunc + its per-block wrapper
+  (reference hdp/threshold.py:52-93)
+* :func:`metrics_array`     <- ``compute_heatwave_metrics`` + the percentile x definition sweep
+  (reference hdp/metric.py:304-369)
+* :func:`hot_days_array`    <- ``indicate_hot_days`` (reference hdp/metric.py:280-301)
+
+plus ``*_host`` variants that take NumPy (host) arrays and run the chunked copy/compute pipeline of
+the library.  PyTorch is used only for device allocations and the current stream.  All compute happens
+in libhdp_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._tables import WindowTables
+
+METRIC_NAMES = ("HWF", "HWN", "HWD", "HWA")      # plane order of the metric output (reference metric.py:336-340)
+
+_workspaces = {}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("hdp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _workspace(device, nbytes: int):
+    """Per-device scratch tensor, grown on demand (the C ABI never allocates)."""
+    torch = _torch()
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces.pop(key, None)
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def _i32(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.size and (a.max() > np.iinfo(np.int32).max or a.min() < np.iinfo(np.int32).min):
+        raise ValueError("index table does not fit int32")
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _hp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check_measure(x, name: str):
+    torch = _torch()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        raise TypeError(f"{name} must be a 2-D float32 CUDA tensor [T, C] (any strides)")
+    if x.numel() and (x.stride(0) < 0 or x.stride(1) < 0):
+        raise ValueError(f"{name} must have non-negative strides")
+
+
+def _strides(x):
+    T, C = x.shape
+    ld_t = x.stride(0) if T > 1 else max(C, 1)
+    ld_c = x.stride(1) if C > 1 else 1
+    return int(ld_t), int(ld_c)
+
+
+def thresholds_array(temps, tables: WindowTables, percentiles: Sequence[float], out=None):
+    """``temps`` f32 ``[T_b, C]`` -> thresholds f64 ``[C, n_doy, P]`` (reference dims (<cells>, doy, percentile))."""
+    torch = _torch()
+    _check_measure(temps, "temps")
+    L = _lib.lib()
+    T_b, C = temps.shape
+    q = np.ascontiguousarray(percentiles, dtype=np.float64).ravel()
+    ti, wr = _i32(tables.time_index), _i32(tables.win_rows)
+    n_doy, n_y, W, P = tables.n_doy, tables.n_y, tables.width, int(q.size)
+    ld_t, ld_c = _strides(temps)
+    if out is None:
+        out = torch.empty((C, n_doy, P), dtype=torch.float64, device=temps.device)
+    elif not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and tuple(out.shape) == (C, n_doy, P)):
+        raise TypeError("out must be a contiguous float64 CUDA tensor [C, n_doy, P]")
+    with torch.cuda.device(temps.device):
+        nbytes = L.hdp_b200_thresholds_workspace_bytes(C, T_b, ld_t, ld_c, n_doy, n_y, W, P)
+        ws = _workspace(temps.device, nbytes)
+        rc = L.hdp_b200_thresholds(temps.data_ptr(), C, T_b, ld_t, ld_c, _hp(ti), _hp(wr), n_doy, n_y, W, _hp(q), P,
+                                   out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_thresholds")
+    return out
+
+
+def _metric_tables(doy_map, defs, season_north, season_south):
+    dm = _i32(doy_map).ravel()
+    df = _i32(defs).reshape(-1, 3)
+    sn, ss = _i32(season_north).reshape(-1, 2), _i32(season_south).reshape(-1, 2)
+    if sn.shape != ss.shape:
+        raise ValueError("northern and southern season tables must have the same number of rows")
+    return dm, df, sn, ss
+
+
+def _check_thr(thr, C):
+    torch = _torch()
+    if not (isinstance(thr, torch.Tensor) and thr.is_cuda and thr.dtype == torch.float64 and thr.dim() == 3
+            and thr.is_contiguous() and thr.shape[0] == C):
+        raise TypeError("thresholds must be a contiguous float64 CUDA tensor [C, n_doy, P]")
+
+
+def metrics_array(measure, thresholds, doy_map, defs, season_north, season_south, is_south=None, out=None):
+    """``measure`` f32 ``[T, C]``, ``thresholds`` f64 ``[C, n_doy, P]`` -> uint16 ``[4, P, D, Y, C]``
+    (planes HWF, HWN, HWD, HWA; the reference's int64 ``[P, D, C, 4, Y]`` is ``out.permute(1, 2, 4, 0, 3)`` widened)."""
+    torch = _torch()
+    _check_measure(measure, "measure")
+    T, C = measure.shape
+    _check_thr(thresholds, C)
+    L = _lib.lib()
+    n_doy, P = int(thresholds.shape[1]), int(thresholds.shape[2])
+    dm, df, sn, ss = _metric_tables(doy_map, defs, season_north, season_south)
+    if dm.size != T:
+        raise ValueError("doy_map must have one entry per time step")
+    D, Y = int(df.shape[0]), int(sn.shape[0])
+    south_t = None
+    if is_south is not None:
+        south_t = torch.as_tensor(np.ascontiguousarray(is_south, dtype=np.uint8) if not isinstance(is_south, torch.Tensor) else is_south)
+        south_t = south_t.to(device=measure.device, dtype=torch.uint8).contiguous()
+        if south_t.numel() != C:
+            raise ValueError("is_south must have one entry per cell")
+    if out is None:
+        out = torch.empty((4, P, D, Y, C), dtype=torch.uint16, device=measure.device)
+    elif not (out.is_cuda and out.dtype == torch.uint16 and out.is_contiguous() and tuple(out.shape) == (4, P, D, Y, C)):
+        raise TypeError("out must be a contiguous uint16 CUDA tensor [4, P, D, Y, C]")
+    ld_t, ld_c = _strides(measure)
+    with torch.cuda.device(measure.device):
+        nbytes = L.hdp_b200_metrics_workspace_bytes(C, T, ld_t, ld_c, n_doy, P, D, Y, _hp(dm))
+        ws = _workspace(measure.device, nbytes)
+        rc = L.hdp_b200_metrics(measure.data_ptr(), C, T, ld_t, ld_c, thresholds.data_ptr(), n_doy, P, _hp(dm),
+                                _hp(df), D, _hp(sn), _hp(ss), Y,
+                                south_t.data_ptr() if south_t is not None else None,
+                                out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_metrics")
+    return out
+
+
+def hot_days_array(measure, thresholds, doy_map):
+    """``indicate_hot_days`` for every percentile: uint8 ``[P, T, C]``."""
+    torch = _torch()
+    _check_measure(measure, "measure")
+    T, C = measure.shape
+    _check_thr(thresholds, C)
+    L = _lib.lib()
+    n_doy, P = int(thresholds.shape[1]), int(thresholds.shape[2])
+    dm = _i32(doy_map).ravel()
+    if dm.size != T:
+        raise ValueError("doy_map must have one entry per time step")
+    out = torch.empty((P, T, C), dtype=torch.uint8, device=measure.device)
+    ld_t, ld_c = _strides(measure)
+    with torch.cuda.device(measure.device):
+        nbytes = L.hdp_b200_metrics_workspace_bytes(C, T, ld_t, ld_c, n_doy, P, 1, 0, _hp(dm))
+        ws = _workspace(measure.device, nbytes)
+        rc = L.hdp_b200_hot_days(measure.data_ptr(), C, T, ld_t, ld_c, thresholds.data_ptr(), n_doy, P, _hp(dm),
+                                 out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_hot_days")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# host-buffer variants (NumPy in, NumPy out; the library pipelines H2D / kernels / D2H over cell chunks)
+# ----------------------------------------------------------------------------------------------
+
+def _host_measure(x: np.ndarray, name: str):
+    x = np.asarray(x)
+    if x.dtype != np.float32 or x.ndim != 2:
+        raise TypeError(f"{name} must be a 2-D float32 array [T, C]")
+    T, C = x.shape
+    ld_t = x.strides[0] // 4 if T > 1 else max(C, 1)
+    ld_c = x.strides[1] // 4 if C > 1 else 1
+    if ld_c != 1 and ld_t != 1:
+        x = np.ascontiguousarray(x)
+        ld_t, ld_c = C, 1
+    return x, int(ld_t), int(ld_c)
+
+
+def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequence[float], out: Optional[np.ndarray] = None) -> np.ndarray:
+    _torch()
+    L = _lib.lib()
+    temps, ld_t, ld_c = _host_measure(temps, "temps")
+    T_b, C = temps.shape
+    q = np.ascontiguousarray(percentiles, dtype=np.float64).ravel()
+    ti, wr = _i32(tables.time_index), _i32(tables.win_rows)
+    if out is None:
+        out = np.empty((C, tables.n_doy, q.size), np.float64)
+    assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (C, tables.n_doy, q.size)
+    rc = L.hdp_b200_thresholds_host(_hp(temps), C, T_b, ld_t, ld_c, _hp(ti), _hp(wr), tables.n_doy, tables.n_y,
+                                    tables.width, _hp(q), int(q.size), _hp(out))
+    _lib.check(rc, "hdp_b200_thresholds_host")
+    return out
+
+
+def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, season_north, season_south,
+                 is_south=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+    _torch()
+    L = _lib.lib()
+    measure, ld_t, ld_c = _host_measure(measure, "measure")
+    T, C = measure.shape
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+    if thr.ndim != 3 or thr.shape[0] != C:
+        raise TypeError("thresholds must be float64 [C, n_doy, P]")
+    n_doy, P = thr.shape[1], thr.shape[2]
+    dm, df, sn, ss = _metric_tables(doy_map, defs, season_north, season_south)
+    if dm.size != T:
+        raise ValueError("doy_map must have one entry per time step")
+    D, Y = df.shape[0], sn.shape[0]
+    south = None if is_south is None else np.ascontiguousarray(is_south, dtype=np.uint8)
+    if out is None:
+        out = np.empty((4, P, D, Y, C), np.uint16)
+    assert out.flags.c_contiguous and out.dtype == np.uint16 and out.shape == (4, P, D, Y, C)
+    rc = L.hdp_b200_metrics_host(_hp(measure), C, T, ld_t, ld_c, _hp(thr), n_doy, P, _hp(dm), _hp(df), D, _hp(sn), _hp(ss), Y,
+                                 _hp(south) if south is not None else None, _hp(out))
+    _lib.check(rc, "hdp_b200_metrics_host")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().hdp_b200_launch_count())

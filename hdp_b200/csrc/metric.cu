@@ -1,0 +1,525 @@
+// metric.cu - path 2: hot-day masks and heatwave metrics for the whole percentile x definition sweep.
+//
+// Replaces (reference = AgentOxygen/HDP v1.0.2):
+//   indicate_hot_days          hdp/metric.py:280-301
+//   index_heatwaves            hdp/metric.py:11-60
+//   heatwave_frequency/number/duration/average   hdp/metric.py:63-172
+//   compute_heatwave_metrics   hdp/metric.py:304-341
+//   compute_heatwave_metrics_wrapper (the percentile x definition x cell sweep)   hdp/metric.py:344-369
+//
+// Two kernels, both HBM-streaming integer/compare work (no tensor cores: nothing here is a contraction):
+//
+//   k_hot_words  (cells x day-of-year block) tiles.  A CTA owns 32 cells and 32 consecutive days of year,
+//                keeps that [32 doy][P][32 cell] threshold tile in shared memory (rounded DOWN to f32, which
+//                preserves the reference's double-precision `measure > threshold` exactly) and walks every
+//                year of the measure through it, so each threshold is fetched from HBM once and each
+//                measure sample once.  Output: one 32-bit word of hot-day bits per (percentile, word, cell).
+//   k_scan       one thread per (cell, percentile), lanes = cells (coalesced).  Walks the hot words in
+//                time order, pops hot runs with bit tricks and feeds each run to all definitions' state
+//                machines held in registers; season accumulators are flushed as u16 when a season closes.
+//                The per-day heatwave id array of the reference is never materialised.
+#include <limits.h>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hdp {
+
+struct DefTable {
+    int min_dur[HDP_B200_MAX_DEFINITIONS];
+    int max_break[HDP_B200_MAX_DEFINITIONS];
+    int max_subs[HDP_B200_MAX_DEFINITIONS];
+};
+
+// ----------------------------------------------------------------------------------------------------
+// k_hot_words
+// ----------------------------------------------------------------------------------------------------
+constexpr int kTileCells = 32;
+constexpr int kTileDoy = 32;
+constexpr int kTilePad = 33;   // [.. ][33]: conflict-free both for the e-major fill and the lane-major reads
+
+template <int PG>
+__global__ void __launch_bounds__(256)
+k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
+            const double *__restrict__ thr, int n_doy, int P,
+            const int4 *__restrict__ words, const int *__restrict__ blk_start, const int *__restrict__ blk_words,
+            int K, uint32_t *__restrict__ hot)
+{
+    extern __shared__ float thr_s[];                      // [32 doy][Ppad][33]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int db = blockIdx.y;
+    const int64_t c0 = (int64_t)blockIdx.x * kTileCells;
+    const int Ppad = (P + PG - 1) / PG * PG;
+    const int nd = min(kTileDoy, n_doy - db * kTileDoy);
+    const int per_cell = kTileDoy * Ppad;
+
+    // Threshold tile: per cell the (doy, percentile) block is contiguous in the reference's [C, n_doy, P] order.
+    for (int idx = tid; idx < kTileCells * per_cell; idx += 256) {
+        int cell = idx / per_cell, e = idx - cell * per_cell;
+        int j = e / Ppad, p = e - j * Ppad;
+        float v = __int_as_float(0x7f800000);             // +inf: never exceeded (padding percentiles / days)
+        if (c0 + cell < C && j < nd && p < P)
+            v = __double2float_rd(thr[((c0 + cell) * n_doy + (db * kTileDoy + j)) * (int64_t)P + p]);
+        thr_s[e * kTilePad + cell] = v;
+    }
+    __syncthreads();
+
+    const int64_t c = c0 + lane;
+    if (c >= C) return;
+    const int w_begin = blk_start[db], w_end = blk_start[db + 1];
+    for (int i = w_begin + warp; i < w_end; i += 8) {
+        const int k = blk_words[i];
+        const int4 w = words[k];                           // {t0, nbits, doy of bit 0, -}
+        const int nb = w.y, jo = w.z & (kTileDoy - 1);
+        const float *xp = x + (int64_t)w.x * ld_t + c;
+        for (int pg = 0; pg < Ppad; pg += PG) {
+            uint32_t m[PG];
+#pragma unroll
+            for (int q = 0; q < PG; q++) m[q] = 0u;
+            const float *ts = thr_s + (jo * Ppad + pg) * kTilePad + lane;
+#pragma unroll 4
+            for (int j = 0; j < nb; j++) {
+                const float v = xp[(int64_t)j * ld_t];
+                const uint32_t bit = 1u << j;
+#pragma unroll
+                for (int q = 0; q < PG; q++)
+                    if (v > ts[(j * Ppad + q) * kTilePad]) m[q] |= bit;     // NaN on either side -> false
+            }
+#pragma unroll
+            for (int q = 0; q < PG; q++)
+                if (pg + q < P) hot[((int64_t)(pg + q) * K + k) * C + c] = m[q];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// k_unpack_mask: hot words -> u8 [P, T, C]   (parity checks of the hot-day mask only)
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_unpack_mask(const uint32_t *__restrict__ hot, int64_t C, int64_t T, int P, int K, const int4 *__restrict__ words,
+              uint8_t *__restrict__ mask)
+{
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= C) return;
+    const int4 w = words[k];
+    for (int p = 0; p < P; p++) {
+        const uint32_t m = hot[((int64_t)p * K + k) * C + c];
+        for (int j = 0; j < w.y; j++) mask[((int64_t)p * T + (w.x + j)) * C + c] = (m >> j) & 1u;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// k_scan
+// ----------------------------------------------------------------------------------------------------
+// Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
+// (the host splits overlapping tables into several passes, one launch each).
+template <int DG>
+__global__ void __launch_bounds__(256)
+k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
+       int P, int D, const __grid_constant__ DefTable defs,
+       const int4 *__restrict__ seasons_north, int n_north, const int4 *__restrict__ seasons_south, int n_south, int Y,
+       const uint8_t *__restrict__ is_south, uint16_t *__restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int p = blockIdx.y * blockDim.y + threadIdx.y;
+    const int d0 = blockIdx.z * DG;
+    if (c >= C || p >= P) return;
+
+    int min_dur[DG], max_break[DG], max_subs[DG];
+    int least_min_dur = INT_MAX;
+#pragma unroll
+    for (int i = 0; i < DG; i++) {
+        const bool live = d0 + i < D;
+        min_dur[i] = live ? defs.min_dur[d0 + i] : INT_MAX;      // padding definitions never label a run
+        max_break[i] = live ? defs.max_break[d0 + i] : INT_MAX;
+        max_subs[i] = live ? defs.max_subs[d0 + i] : 0;
+        least_min_dur = min(least_min_dur, min_dur[i]);
+    }
+
+    const bool south = is_south != nullptr && is_south[c] != 0;
+    const int4 *seas = south ? seasons_south : seasons_north;
+    const int n_seasons = south ? n_south : n_north;
+    int ys = 0;
+    int a_cur = INT_MAX, b_cur = INT_MAX, row_cur = 0;
+    if (n_seasons > 0) { const int4 s4 = seas[0]; a_cur = s4.x; b_cur = s4.y; row_cur = s4.z; }
+
+    // per-definition state (registers): reference's in_heatwave / sub_events (metric.py:34-36), and the open
+    // season's accumulators.  cnt = days carrying the current heatwave id inside the open season.
+    uint32_t inhw = 0u;
+    int sub[DG], cnt[DG], hwf[DG], hwn[DG], hwd[DG];
+#pragma unroll
+    for (int i = 0; i < DG; i++) { sub[i] = 0; cnt[i] = 0; hwf[i] = 0; hwn[i] = 0; hwd[i] = 0; }
+
+    const int64_t plane = (int64_t)P * D * Y * C;                 // one metric
+    auto flush = [&]() {                                          // close season `ys`
+#pragma unroll
+        for (int i = 0; i < DG; i++) {
+            if (d0 + i < D) {
+                const int64_t o = (((int64_t)p * D + (d0 + i)) * Y + row_cur) * C + c;
+                out[o] = (uint16_t)hwf[i];
+                out[o + plane] = (uint16_t)hwn[i];
+                out[o + 2 * plane] = (uint16_t)hwd[i];
+                out[o + 3 * plane] = (uint16_t)(hwn[i] > 0 ? hwf[i] / hwn[i] : 0);   // trunc(mean), metric.py:340
+            }
+            cnt[i] = 0; hwf[i] = 0; hwn[i] = 0; hwd[i] = 0;
+        }
+        ys++;
+        if (ys < n_seasons) { const int4 s4 = seas[ys]; a_cur = s4.x; b_cur = s4.y; row_cur = s4.z; }
+        else { a_cur = INT_MAX; b_cur = INT_MAX; }
+    };
+
+    int prev_e = -(1 << 29);      // end of the previous hot run
+    int run_start = -1;           // start of the hot run still open at the end of the previous word
+    const uint32_t *hp = hot + (int64_t)p * K * C + c;
+
+    uint32_t m_next = K > 0 ? hp[0] : 0u;
+    for (int k = 0; k <= K; k++) {
+        // word K is a virtual cold day at t = T that closes a run reaching the end of the series
+        const uint32_t m = m_next;
+        int t0 = T, nb = 1;
+        if (k < K) { const int4 w = words[k]; t0 = w.x; nb = w.y; }
+        m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
+
+        const uint32_t carry = run_start >= 0 ? 1u : 0u;
+        const uint32_t prev = (m << 1) | carry;                   // bit i = day i-1 hot
+        uint32_t starts = m & ~prev;
+        uint32_t ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        while (ends) {
+            const int e = t0 + __ffs(ends) - 1;
+            ends &= ends - 1;
+            int s = run_start;
+            if (s < 0) { s = t0 + __ffs(starts) - 1; starts &= starts - 1; }
+            run_start = -1;
+
+            // ---- one hot run [s, e): reference index_heatwaves branches A-D, metric.py:39-58 ----
+            const int len = e - s, gap = s - prev_e;
+            prev_e = e;
+            if (inhw == 0u && len < least_min_dur) continue;      // no definition can react
+            uint32_t lab = 0u;
+#pragma unroll
+            for (int i = 0; i < DG; i++) {
+                const uint32_t bit = 1u << i;
+                if (gap > max_break[i]) inhw &= ~bit;             // B: the break before this run was too long
+                const bool ge = len >= min_dur[i];
+                if (!(inhw & bit)) {                              // A: a new heatwave starts (or nothing happens)
+                    if (ge) { inhw |= bit; lab |= bit; cnt[i] = 0; }
+                } else if (sub[i] < max_subs[i]) {                // C: subsequent event of the current heatwave
+                    sub[i]++;
+                    lab |= bit;
+                } else {                                          // D: subsequent events used up
+                    if (ge) { lab |= bit; cnt[i] = 0; }
+                    else inhw &= ~bit;
+                    sub[i] = 0;
+                }
+            }
+            if (lab == 0u) continue;
+            // ---- season accounting: HWF / HWN / HWD (metric.py:63-137) over [s, e) ----
+            while (b_cur <= s) flush();
+            while (a_cur < e) {
+                const int days = min(e, b_cur) - max(s, a_cur);
+                if (days > 0) {
+#pragma unroll
+                    for (int i = 0; i < DG; i++) {
+                        if (lab & (1u << i)) {
+                            hwn[i] += (cnt[i] == 0);
+                            cnt[i] += days;
+                            hwf[i] += days;
+                            hwd[i] = max(hwd[i], cnt[i]);
+                        }
+                    }
+                }
+                if (e <= b_cur) break;
+                flush();
+            }
+        }
+        if (starts) run_start = t0 + __ffs(starts) - 1;           // at most one start is left: the run stays open
+    }
+    while (ys < n_seasons) flush();
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------
+struct WordPlan {
+    std::vector<int4> words;        // {t0, nbits, doy of bit 0, 0}
+    std::vector<int> blk_start;     // [n_blk + 1]
+    std::vector<int> blk_words;     // word ids grouped by day-of-year block
+    int n_blk = 0;
+};
+
+// Cuts the time axis into words of <= 32 consecutive days whose days of year are consecutive and stay
+// inside one 32-day block of the day-of-year axis (so that every word of a block shares one threshold tile).
+static int build_words(const int32_t *doy_map, int64_t T, int n_doy, WordPlan &plan)
+{
+    plan.n_blk = (n_doy + kTileDoy - 1) / kTileDoy;
+    int64_t t = 0;
+    while (t < T) {
+        const int d0 = doy_map[t];
+        if (d0 < 0 || d0 >= n_doy) return HDP_B200_ERR_INVALID;
+        int nb = 1;
+        while (t + nb < T && nb < 32) {
+            const int d = doy_map[t + nb];
+            if (d != d0 + nb || (d & (kTileDoy - 1)) == 0) break;
+            nb++;
+        }
+        plan.words.push_back(make_int4((int)t, nb, d0, 0));
+        t += nb;
+    }
+    const int K = (int)plan.words.size();
+    plan.blk_start.assign(plan.n_blk + 1, 0);
+    for (int k = 0; k < K; k++) plan.blk_start[plan.words[k].z / kTileDoy + 1]++;
+    for (int b = 0; b < plan.n_blk; b++) plan.blk_start[b + 1] += plan.blk_start[b];
+    plan.blk_words.resize(K);
+    std::vector<int> fill(plan.blk_start.begin(), plan.blk_start.end() - 1);
+    for (int k = 0; k < K; k++) plan.blk_words[fill[plan.words[k].z / kTileDoy]++] = k;
+    return HDP_B200_OK;
+}
+
+static int64_t words_upper_bound(int64_t T, int n_doy)
+{
+    // regular daily calendars: every (partial) year contributes at most n_blk + 1 words
+    const int64_t n_blk = (n_doy + kTileDoy - 1) / kTileDoy;
+    return (T / std::max(n_doy, 1) + 2) * (n_blk + 1) + 1;
+}
+
+static int64_t count_words(const int32_t *doy_map, int64_t T)
+{
+    int64_t K = 0, t = 0;
+    while (t < T) {
+        const int d0 = doy_map[t];
+        int nb = 1;
+        while (t + nb < T && nb < 32) {
+            const int d = doy_map[t + nb];
+            if (d != d0 + nb || (d & (kTileDoy - 1)) == 0) break;
+            nb++;
+        }
+        K++;
+        t += nb;
+    }
+    return K;
+}
+
+static int pick_pg(int P)
+{
+    const int cand[] = {4, 8, 10, 16, 20};
+    int best = 4, best_waste = INT_MAX;
+    for (int pg : cand) {
+        const int waste = (P + pg - 1) / pg * pg - P;
+        if (waste < best_waste || (waste == best_waste && pg > best && pg <= 20)) { best = pg; best_waste = waste; }
+    }
+    return best;
+}
+
+static int pick_dg(int D)
+{
+    const int cand[] = {2, 4, 6, 8};
+    int best = 2, best_waste = INT_MAX;
+    for (int dg : cand) {
+        const int waste = (D + dg - 1) / dg * dg - D;
+        if (waste < best_waste || (waste == best_waste && dg > best)) { best = dg; best_waste = waste; }
+    }
+    return best;
+}
+
+struct Layout {
+    size_t total = 0;
+    float *xn = nullptr;
+    int4 *words = nullptr;
+    int *blk_start = nullptr, *blk_words = nullptr;
+    int4 *seasons = nullptr;
+    uint32_t *hot = nullptr;
+};
+
+static Layout carve(void *ws, size_t ws_bytes, int64_t C, int64_t T, bool need_norm, int64_t K, int n_doy, int P, int Y)
+{
+    Layout L;
+    Carver cv(ws, ws_bytes);
+    if (need_norm) L.xn = cv.take<float>((size_t)C * T);
+    L.words = cv.take<int4>((size_t)K + 1);
+    L.blk_start = cv.take<int>((size_t)(n_doy + kTileDoy - 1) / kTileDoy + 1);
+    L.blk_words = cv.take<int>((size_t)K + 1);
+    L.seasons = cv.take<int4>((size_t)2 * (Y + 1));
+    L.hot = cv.take<uint32_t>((size_t)P * K * C);
+    L.total = cv.off;
+    return L;
+}
+
+static bool bad_dims(int64_t C, int64_t T, int n_doy, int P)
+{
+    return C < 0 || T < 0 || n_doy <= 0 || P <= 0 || T > 0x3fffffff;
+}
+
+// Runs k_hot_words; on success *plan_out/*L_out describe what lives in the workspace.
+static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                         const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                         int Y, void *ws, size_t ws_bytes, cudaStream_t st, WordPlan &plan, Layout &L)
+{
+    int rc = build_words(h_doy_map, T, n_doy, plan);
+    if (rc != HDP_B200_OK) return rc;
+    const int K = (int)plan.words.size();
+    const bool need_norm = ld_c != 1;
+    L = carve(ws, ws_bytes, C, T, need_norm, K, n_doy, P, Y);
+    if (ws == nullptr || L.total > ws_bytes) return HDP_B200_ERR_WORKSPACE;
+    if (C == 0 || T == 0) return HDP_B200_OK;
+    const float *x = d_measure;
+    if (need_norm) {
+        rc = normalize_layout(d_measure, C, T, ld_t, ld_c, L.xn, st);
+        if (rc != HDP_B200_OK) return rc;
+        x = L.xn;
+        ld_t = C;
+    }
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.words, plan.words.data(), sizeof(int4) * K, cudaMemcpyHostToDevice, st));
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_start, plan.blk_start.data(), sizeof(int) * plan.blk_start.size(), cudaMemcpyHostToDevice, st));
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_words, plan.blk_words.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
+
+    const int pg = pick_pg(P);
+    const int Ppad = (P + pg - 1) / pg * pg;
+    const size_t smem = (size_t)kTileDoy * Ppad * kTilePad * sizeof(float);
+    dim3 grid((unsigned)((C + kTileCells - 1) / kTileCells), (unsigned)plan.n_blk);
+#define HDP_LAUNCH_HOT(PG)                                                                                         \
+    do {                                                                                                           \
+        HDP_CUDA_TRY(cudaFuncSetAttribute(k_hot_words<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_hot_words<PG><<<grid, 256, smem, st>>>(x, C, ld_t, d_thr, n_doy, P, L.words, L.blk_start, L.blk_words, K, L.hot); \
+    } while (0)
+    switch (pg) {
+    case 4: HDP_LAUNCH_HOT(4); break;
+    case 8: HDP_LAUNCH_HOT(8); break;
+    case 10: HDP_LAUNCH_HOT(10); break;
+    case 16: HDP_LAUNCH_HOT(16); break;
+    default: HDP_LAUNCH_HOT(20); break;
+    }
+#undef HDP_LAUNCH_HOT
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
+}
+
+// Python-slice semantics of hw_ts[a:b] (metric.py:79,100,122,157) resolved to 0 <= lo <= hi <= T.
+static void clamp_season(int64_t a, int64_t b, int64_t T, int &lo, int &hi)
+{
+    if (a < 0) { a += T; if (a < 0) a = 0; }
+    if (b < 0) { b += T; if (b < 0) b = 0; }
+    if (a > T) a = T;
+    if (b > T) b = T;
+    if (b < a) b = a;
+    lo = (int)a; hi = (int)b;
+}
+
+}  // namespace hdp
+
+using namespace hdp;
+
+extern "C" {
+
+size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                                        int n_doy, int P, int D, int Y, const int32_t *h_doy_map)
+{
+    (void)ld_t; (void)D;
+    if (bad_dims(C, T, n_doy, P) || Y < 0) return 0;
+    const int64_t K = h_doy_map ? count_words(h_doy_map, T) : words_upper_bound(T, n_doy);
+    return carve(nullptr, 0, C, T, ld_c != 1, K, n_doy, P, Y).total;
+}
+
+int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                      const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                      uint8_t *d_mask, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (bad_dims(C, T, n_doy, P) || !h_doy_map && T > 0) return HDP_B200_ERR_INVALID;
+    if (C > 0 && T > 0 && (!d_measure || !d_thr || !d_mask)) return HDP_B200_ERR_INVALID;
+    if (P > HDP_B200_MAX_PERCENTILES) return HDP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    WordPlan plan;
+    Layout L;
+    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, 0, d_workspace, workspace_bytes, st, plan, L);
+    if (rc != HDP_B200_OK || C == 0 || T == 0) return rc;
+    const int K = (int)plan.words.size();
+    dim3 grid((unsigned)((C + 255) / 256), (unsigned)K);
+    if (K > 65535) return HDP_B200_ERR_UNSUPPORTED;
+    k_unpack_mask<<<grid, 256, 0, st>>>(L.hot, C, T, P, K, L.words, d_mask);
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
+}
+
+int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                     const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                     const int32_t *h_defs, int D,
+                     const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                     const uint8_t *d_is_south, uint16_t *d_out,
+                     void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (bad_dims(C, T, n_doy, P) || D <= 0 || Y < 0) return HDP_B200_ERR_INVALID;
+    if ((T > 0 && !h_doy_map) || !h_defs || (Y > 0 && (!h_season_north || !h_season_south))) return HDP_B200_ERR_INVALID;
+    if (C > 0 && T > 0 && (!d_measure || !d_thr)) return HDP_B200_ERR_INVALID;
+    if (C > 0 && Y > 0 && !d_out) return HDP_B200_ERR_INVALID;
+    if (P > HDP_B200_MAX_PERCENTILES || D > HDP_B200_MAX_DEFINITIONS) return HDP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // season tables: clamp, then split into passes of sorted, disjoint seasons per hemisphere
+    struct Season { int a, b, row; };
+    std::vector<std::vector<Season>> passes[2];
+    for (int h = 0; h < 2; h++) {
+        const int32_t *tab = h == 0 ? h_season_north : h_season_south;
+        std::vector<Season> all(Y);
+        for (int y = 0; y < Y; y++) {
+            clamp_season(tab[2 * y], tab[2 * y + 1], T, all[y].a, all[y].b);
+            all[y].row = y;
+            if (all[y].b - all[y].a > 65535) return HDP_B200_ERR_UNSUPPORTED;
+        }
+        std::stable_sort(all.begin(), all.end(), [](const Season &l, const Season &r) { return l.a < r.a; });
+        for (const Season &s : all) {
+            size_t i = 0;
+            for (; i < passes[h].size(); i++)
+                if (passes[h][i].back().b <= s.a) break;
+            if (i == passes[h].size()) passes[h].emplace_back();
+            passes[h][i].push_back(s);
+        }
+    }
+    const size_t n_pass = std::max(passes[0].size(), passes[1].size());
+
+    WordPlan plan;
+    Layout L;
+    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, Y, d_workspace, workspace_bytes, st, plan, L);
+    if (rc != HDP_B200_OK || C == 0 || Y == 0) return rc;
+    const int K = (int)plan.words.size();
+
+    DefTable defs;
+    for (int i = 0; i < HDP_B200_MAX_DEFINITIONS; i++) {
+        defs.min_dur[i] = i < D ? h_defs[3 * i] : INT_MAX;
+        defs.max_break[i] = i < D ? h_defs[3 * i + 1] : INT_MAX;
+        defs.max_subs[i] = i < D ? h_defs[3 * i + 2] : 0;
+    }
+    const int dg = pick_dg(D);
+    const int pw = std::min(P, 8);
+    dim3 block(32, pw);
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((P + pw - 1) / pw), (unsigned)((D + dg - 1) / dg));
+
+    // all passes of both hemispheres live side by side in the workspace: north passes, then south passes
+    std::vector<int4> tab;
+    std::vector<size_t> off[2];
+    for (int h = 0; h < 2; h++)
+        for (const auto &pass : passes[h]) {
+            off[h].push_back(tab.size());
+            for (const Season &s : pass) tab.push_back(make_int4(s.a, s.b, s.row, 0));
+        }
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.seasons, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice, st));
+    for (size_t ip = 0; ip < n_pass; ip++) {
+        const int4 *sn = ip < passes[0].size() ? L.seasons + off[0][ip] : L.seasons;
+        const int4 *ss = ip < passes[1].size() ? L.seasons + off[1][ip] : L.seasons;
+        const int nn = ip < passes[0].size() ? (int)passes[0][ip].size() : 0;
+        const int ns = ip < passes[1].size() ? (int)passes[1][ip].size() : 0;
+#define HDP_LAUNCH_SCAN(DG) \
+        k_scan<DG><<<grid, block, 0, st>>>(L.hot, C, K, (int)T, L.words, P, D, defs, sn, nn, ss, ns, Y, d_is_south, d_out)
+        switch (dg) {
+        case 2: HDP_LAUNCH_SCAN(2); break;
+        case 4: HDP_LAUNCH_SCAN(4); break;
+        case 6: HDP_LAUNCH_SCAN(6); break;
+        default: HDP_LAUNCH_SCAN(8); break;
+        }
+#undef HDP_LAUNCH_SCAN
+        HDP_LAUNCH_CHECK();
+    }
+    return HDP_B200_OK;
+}
+
+}  // extern "C"

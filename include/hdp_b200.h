@@ -96,8 +96,9 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
  *                 the reference's int64 (percentile, definition, <cells>, metric, year) array is
  *                 out[m][p][d][y][c] widened.  Every value is <= the longest season, which must be < 65536.
  * ------------------------------------------------------------------------------------------------- */
+/* h_doy_map may be NULL: the size is then an upper bound for regular daily calendars. */
 size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                                        int n_doy, int P, int D, int Y);
+                                        int n_doy, int P, int D, int Y, const int32_t *h_doy_map);
 
 int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                      const double *d_thr, int n_doy, int P,

@@ -149,7 +149,7 @@ def metrics_batch(measure_tc, thresholds_cdp, doy_map, defs, seasons_north, seas
     dm = _c(doy_map, np.int64)
     df = _c(defs, np.int64).reshape(-1, 3)
     sn, ss = _c(seasons_north, np.int64), _c(seasons_south, np.int64)
-    south = _c(is_south, np.uint8)
+    south = np.zeros(C, np.uint8) if is_south is None else _c(is_south, np.uint8)
     Y = sn.shape[0]
     out = np.empty((P, df.shape[0], C, 4, Y), np.int64)
     ld_t, ld_c = (s // 4 for s in meas.strides)

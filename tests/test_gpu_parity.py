@@ -1,0 +1,209 @@
+"""GPU parity: the CUDA paths (through the C ABI) against the reference's golden fixtures and the CPU oracle.
+
+Integer metrics and the hot-day mask must be bit-exact; thresholds are compared at 0 ulp in float64
+(stated tolerance: bit-exact up to the sign of zero; NaN positions identical)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import bits_equal
+from kat import INDEX_KAT
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def core():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hdp_b200 import _core
+    return _core
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def ref_layout(out_u16):
+    """uint16 [4, P, D, Y, C] -> the reference's int64 [P, D, C, 4, Y]."""
+    return out_u16.cpu().numpy().astype(np.int64).transpose(1, 2, 4, 0, 3)
+
+
+# ------------------------------------------------------------------------------------------ path 1
+@pytest.mark.parametrize("name", ["noleap6_r7", "std9_r15", "d360_r2", "noleap3_r0", "noleap30_r7", "special_r3"])
+def test_thresholds_golden(core, golden_percentiles, name):
+    from hdp_b200 import _tables as tb
+    g = golden_percentiles
+    wt = tb.window_tables(g[f"{name}.dayofyr"], int(g[f"{name}.radius"]))
+    got = core.thresholds_array(dev(g[f"{name}.x"]), wt, g[f"{name}.q"]).cpu().numpy()
+    assert bits_equal(got, g[f"{name}.out"])
+
+
+def test_thresholds_layouts_and_host(core, golden_percentiles):
+    from hdp_b200 import _tables as tb
+    g, name = golden_percentiles, "noleap6_r7"
+    wt = tb.window_tables(g[f"{name}.dayofyr"], 7)
+    x, q, want = g[f"{name}.x"], g[f"{name}.q"], g[f"{name}.out"]
+    xt = dev(x.T.copy()).t()                                  # [T, C] view of a time-contiguous [C, T] array
+    assert xt.stride(0) == 1
+    assert bits_equal(core.thresholds_array(xt, wt, q).cpu().numpy(), want)
+    assert bits_equal(core.thresholds_host(x, wt, q), want)
+    assert bits_equal(core.thresholds_host(np.ascontiguousarray(x.T).T, wt, q), want)
+
+
+def test_thresholds_random_vs_oracle(core):
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(7)
+    ax = tb.TimeAxis.daily((1961, 1, 1), 5 * 365, "noleap")
+    wt = tb.window_tables(ax.dayofyr, 7)
+    C = 203                                                   # ragged: not a multiple of any tile
+    x = (15 + 10 * np.sin(2 * np.pi * ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(ax), C))).astype(np.float32)
+    x[rng.integers(0, len(ax), 20), rng.integers(0, C, 20)] = np.nan
+    q = np.array([0.0, 0.1, 0.5, 0.9, 0.95, 0.999, 1.0])
+    want = oracle.thresholds_batch(x, wt.window_samples(), q)
+    got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
+    assert bits_equal(got, want)
+
+
+def test_thresholds_errors(core):
+    from hdp_b200 import _tables as tb, _lib
+    ax = tb.TimeAxis.daily((1961, 1, 1), 2 * 365, "noleap")
+    wt = tb.window_tables(ax.dayofyr, 1)
+    x = torch.zeros((len(ax), 4), dtype=torch.float32, device="cuda")
+    with pytest.raises(_lib.HdpB200Error) as e:
+        core.thresholds_array(x, wt, [0.5, 1.5])              # reference: ValueError('Quantiles must be in the range [0, 1]')
+    assert e.value.code == -1
+    with pytest.raises(_lib.HdpB200Error):
+        core.thresholds_array(x, wt, [float("nan")])
+    assert core.thresholds_array(x[:, :0], wt, [0.5]).shape == (0, 365, 1)
+
+
+# ------------------------------------------------------------------------------------------ path 2
+@pytest.mark.parametrize("name", ["noleap12", "std7", "noleap_mid5"])
+def test_metrics_golden(core, golden_metrics, name):
+    g = golden_metrics
+    args = (g[f"{name}.doy_map"], g[f"{name}.defs"], g[f"{name}.north"], g[f"{name}.south"], g[f"{name}.is_south"])
+    out = core.metrics_array(dev(g[f"{name}.x"]), dev(g[f"{name}.thr"]), *args)
+    assert np.array_equal(ref_layout(out), g[f"{name}.out"])
+    # host-buffer entry point, and a time-contiguous device layout
+    out_h = core.metrics_host(g[f"{name}.x"], g[f"{name}.thr"], *args)
+    assert np.array_equal(out_h, out.cpu().numpy())
+    xt = dev(g[f"{name}.x"].T.copy()).t()
+    assert np.array_equal(core.metrics_array(xt, dev(g[f"{name}.thr"]), *args).cpu().numpy(), out_h)
+
+
+@pytest.mark.parametrize("name", ["noleap12", "std7", "noleap_mid5"])
+def test_hot_days_golden_inputs(core, golden_metrics, name):
+    g = golden_metrics
+    x, thr, dm = g[f"{name}.x"], g[f"{name}.thr"], g[f"{name}.doy_map"]
+    got = core.hot_days_array(dev(x), dev(thr), dm).cpu().numpy()
+    for c in range(x.shape[1]):
+        for p in range(thr.shape[2]):
+            assert np.array_equal(got[p, :, c].astype(bool), oracle.indicate_hot_days(x[:, c], thr[c, :, p], dm))
+
+
+def test_hot_days_f32_vs_f64_boundary(core):
+    # thresholds a hair above / below / equal to representable f32 values: the f32 round-down trick must
+    # agree with the reference's double-precision compare ("f32-vs-f64 compare")
+    rng = np.random.default_rng(3)
+    n_doy, T, C = 40, 80, 64
+    base = rng.standard_normal((n_doy, C)).astype(np.float32)
+    thr = base.astype(np.float64)
+    thr[::3] = np.nextafter(thr[::3], np.inf)
+    thr[1::3] = np.nextafter(thr[1::3], -np.inf)
+    thr[5] = np.nan
+    thr[6] = np.inf
+    thr[7] = -np.inf
+    thr[8] = 1e300
+    thr[9] = -1e300
+    dm = np.arange(T) % n_doy
+    x = base[dm].copy()
+    x[::2] = np.nextafter(x[::2], np.float32(np.inf))
+    x[3] = np.nan
+    x[4] = np.inf
+    x[5 + n_doy] = -np.inf
+    thr_cdp = np.ascontiguousarray(thr.T[:, :, None])         # [C, n_doy, 1]
+    got = core.hot_days_array(dev(x), dev(thr_cdp), dm).cpu().numpy()[0]
+    want = np.stack([oracle.indicate_hot_days(x[:, c], thr_cdp[c, :, 0], dm) for c in range(C)], axis=1)
+    assert np.array_equal(got.astype(bool), want)
+
+
+def _mask_case(core, masks, defs, north, south, is_south):
+    """Feed 0/1 masks as the measure against a 0.5 threshold: the hot-day mask IS the input."""
+    masks = np.asarray(masks)
+    T, C = masks.shape
+    x = masks.astype(np.float32)
+    thr = np.full((C, 1, 1), 0.5)
+    dm = np.zeros(T, np.int64)
+    out = ref_layout(core.metrics_array(dev(x), dev(thr), dm, defs, north, south, is_south))
+    want = oracle.metrics_batch(x, thr, dm, defs, north, south, is_south)
+    assert np.array_equal(out, want)
+    return out
+
+
+def test_reference_kat_masks(core):
+    # the reference's own index_heatwaves vectors (hdp/tests/test_index_heatwaves.py), pushed through the
+    # metric kernel: HWF/HWN/HWD/HWA over one whole-series season and over a two-season split
+    for mask, expectations in INDEX_KAT:
+        T = mask.size
+        defs = [list(d) for d, _ in expectations]
+        for ranges in ([[0, T]], [[0, 8], [8, T]], [[2, 5], [5, 6], [9, T - 1]]):
+            out = _mask_case(core, mask[:, None].repeat(3, 1), defs, ranges, ranges, [0, 1, 0])
+            for k, (d, ids) in enumerate(expectations):
+                ids = np.asarray(ids)
+                assert np.array_equal(out[0, k, 0, 0], oracle.heatwave_frequency(ids, ranges))
+                assert np.array_equal(out[0, k, 0, 1], oracle.heatwave_number(ids, ranges))
+                assert np.array_equal(out[0, k, 0, 2], oracle.heatwave_duration(ids, ranges))
+
+
+def test_overlapping_and_odd_seasons(core):
+    rng = np.random.default_rng(11)
+    T, C = 300, 40
+    masks = rng.random((T, C)) < 0.45
+    defs = [[1, 1, 1], [3, 0, 0], [2, 2, 3], [0, 0, 1]]
+    north = [[0, 5], [0, 10], [20, 30], [42, 50], [100, 100], [-50, -1], [250, 400]]     # overlapping, empty, negative, beyond T
+    south = [[10, 60], [60, 61], [61, 200], [150, 260], [0, 300], [299, 300], [5, 5]]
+    _mask_case(core, masks, defs, north, south, rng.integers(0, 2, C))
+
+
+def test_long_runs_span_seasons(core):
+    T, C = 2000, 33
+    masks = np.ones((T, C), bool)
+    masks[700, :] = False
+    masks[1500:1503, 1::2] = False
+    seasons = [[100, 250], [465, 615], [830, 980], [1195, 1345], [1560, 1710]]
+    _mask_case(core, masks, [[3, 0, 0], [3, 1, 1], [5, 2, 0]], seasons, seasons, None)
+
+
+def test_metrics_random_sweep_vs_oracle(core):
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(5)
+    ax = tb.TimeAxis.date_range("2001-01-01", "2009-12-31", "standard")
+    T, C, P = len(ax), 171, 10
+    doy = ax.dayofyr
+    x = (15 + 10 * np.sin(2 * np.pi * (doy[:, None] - 110) / 365) + 4 * rng.standard_normal((T, C))
+         + 3 * np.arange(T)[:, None] / T).astype(np.float32)
+    x[rng.integers(0, T, 50), rng.integers(0, C, 50)] = np.nan
+    thr = 15 + 10 * np.sin(2 * np.pi * (np.arange(366)[None, :, None] - 110) / 365) + np.linspace(1, 9, P)[None, None, :] \
+        + rng.standard_normal((C, 366, 1))
+    st = tb.hemisphere_ranges(ax)
+    defs = [[a, b, c] for a in (3, 4, 5, 6) for b in (0, 1, 2) for c in (0, 1)]       # the 24-definition grid
+    is_south = (np.arange(C) < C // 2).astype(np.uint8)
+    args = (tb.doy_map(doy), defs, st.north, st.south, is_south)
+    out = core.metrics_array(dev(x), dev(thr), *args)
+    want = oracle.metrics_batch(x, thr, *args)
+    assert np.array_equal(ref_layout(out), want)
+    hwf, hwn, hwd, hwa = (out[i].cpu().numpy().astype(np.int64) for i in range(4))
+    assert (hwf >= hwd).all() and (hwd >= hwa).all()           # reference invariant, hdp/tests/test_workflow.py:52-53
+    assert np.array_equal(hwa, np.where(hwn > 0, hwf // np.maximum(hwn, 1), 0))
+
+
+def test_metrics_tiny_and_empty(core):
+    one = _mask_case(core, [[1]], [[1, 0, 0], [2, 0, 0]], [[0, 1]], [[0, 1]], None)
+    assert one[0, :, 0, 0, 0].tolist() == [1, 0]
+    x = torch.zeros((10, 0), dtype=torch.float32, device="cuda")
+    thr = torch.zeros((0, 1, 2), dtype=torch.float64, device="cuda")
+    out = core.metrics_array(x, thr, np.zeros(10, int), [[3, 0, 0]], [[0, 10]], [[0, 10]])
+    assert tuple(out.shape) == (4, 2, 1, 1, 0)

@@ -231,3 +231,20 @@ def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, sea
 
 def launch_count() -> int:
     return int(_lib.lib().hdp_b200_launch_count())
+
+
+KERNEL_NAMES = {1: "normalize", 2: "k_thr_generic", 3: "k_hot_words", 4: "k_scan", 5: "k_unpack_mask",
+                6: "k_thr_sort", 7: "k_thr_select"}
+
+
+def timing_enable(on: bool) -> None:
+    """Bracket every kernel launch of the library with CUDA events on its launching stream."""
+    _lib.lib().hdp_b200_timing_enable(1 if on else 0)
+
+
+def timing_read(cap: int = 65536):
+    """[(kernel name, milliseconds), ...] of the launches recorded since the last read (waits for them)."""
+    ids = (ctypes.c_int * cap)()
+    ms = (ctypes.c_float * cap)()
+    n = _lib.lib().hdp_b200_timing_read(ids, ms, cap)
+    return [(KERNEL_NAMES.get(ids[i], str(ids[i])), float(ms[i])) for i in range(n)]

@@ -1,9 +1,36 @@
 // abi.cu - library-level entry points and the layout-normalising copy.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace hdp {
 
 int64_t g_launch_count = 0;
+
+// ---- per-kernel timing: event pairs recorded on the launching stream, read back on request ----
+struct TimedLaunch { int id; cudaEvent_t start, stop; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::mutex g_timed_mu;
+
+KernelTimer::KernelTimer(int id, cudaStream_t s) : on(g_timing), st(s), slot(-1)
+{
+    if (!on) return;
+    TimedLaunch t{id, nullptr, nullptr};
+    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(t.start, st);
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    slot = (int)g_timed.size();
+    g_timed.push_back(t);
+}
+
+KernelTimer::~KernelTimer()
+{
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_timed_mu);
+    cudaEventRecord(g_timed[slot].stop, st);
+}
 
 // [C, T] (time-contiguous, ld_t == 1) -> [T, C]: 32x32 tiles through shared memory so that both the
 // reads (along t) and the writes (along c) are coalesced.
@@ -40,6 +67,7 @@ __global__ void __launch_bounds__(256) k_gather_strided(const float *__restrict_
 int normalize_layout(const float *src, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c, float *dst, cudaStream_t st)
 {
     if (C == 0 || T == 0) return HDP_B200_OK;
+    KernelTimer timer(kNormalize, st);
     if (ld_t == 1 && (T + 31) / 32 < 2147483647LL && (C + 31) / 32 <= 65535) {
         dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32));
         k_transpose_ct<<<grid, 256, 0, st>>>(src, C, T, ld_c, dst);
@@ -59,6 +87,27 @@ extern "C" {
 int hdp_b200_abi_version(void) { return HDP_B200_ABI_VERSION; }
 
 int64_t hdp_b200_launch_count(void) { return hdp::g_launch_count; }
+
+void hdp_b200_timing_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(hdp::g_timed_mu);
+    hdp::g_timing = on != 0;
+}
+
+int hdp_b200_timing_read(int *ids, float *ms, int cap)
+{
+    std::lock_guard<std::mutex> lk(hdp::g_timed_mu);
+    int n = 0;
+    for (auto &t : hdp::g_timed) {
+        float v = -1.0f;
+        if (cudaEventSynchronize(t.stop) == cudaSuccess) cudaEventElapsedTime(&v, t.start, t.stop);
+        if (n < cap) { if (ids) ids[n] = t.id; if (ms) ms[n] = v; n++; }
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    hdp::g_timed.clear();
+    return n;
+}
 
 const char *hdp_b200_strerror(int code)
 {

@@ -28,6 +28,16 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? HDP_B200_OK : 
         if (_e != cudaSuccess) return (int)_e;               \
     } while (0)
 
+// Optional per-kernel CUDA-event timing (hdp_b200_timing_enable / hdp_b200_timing_read).
+enum KernelId { kNormalize = 1, kThrGeneric = 2, kHotWords = 3, kScan = 4, kUnpackMask = 5, kThrSort = 6, kThrSelect = 7 };
+struct KernelTimer {
+    bool on;
+    cudaStream_t st;
+    int slot;
+    KernelTimer(int id, cudaStream_t st);
+    ~KernelTimer();
+};
+
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
 

@@ -378,6 +378,7 @@ static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t l
     const int Ppad = (P + pg - 1) / pg * pg;
     const size_t smem = (size_t)kTileDoy * Ppad * kTilePad * sizeof(float);
     dim3 grid((unsigned)((C + kTileCells - 1) / kTileCells), (unsigned)plan.n_blk);
+    KernelTimer timer(kHotWords, st);
 #define HDP_LAUNCH_HOT(PG)                                                                                         \
     do {                                                                                                           \
         HDP_CUDA_TRY(cudaFuncSetAttribute(k_hot_words<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -436,6 +437,7 @@ int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t
     const int K = (int)plan.words.size();
     dim3 grid((unsigned)((C + 255) / 256), (unsigned)K);
     if (K > 65535) return HDP_B200_ERR_UNSUPPORTED;
+    KernelTimer timer(kUnpackMask, st);
     k_unpack_mask<<<grid, 256, 0, st>>>(L.hot, C, T, P, K, L.words, d_mask);
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;
@@ -508,6 +510,7 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         const int4 *ss = ip < passes[1].size() ? L.seasons + off[1][ip] : L.seasons;
         const int nn = ip < passes[0].size() ? (int)passes[0][ip].size() : 0;
         const int ns = ip < passes[1].size() ? (int)passes[1][ip].size() : 0;
+        KernelTimer timer(kScan, st);
 #define HDP_LAUNCH_SCAN(DG) \
         k_scan<DG><<<grid, block, 0, st>>>(L.hot, C, K, (int)T, L.words, P, D, defs, sn, nn, ss, ns, Y, d_is_south, d_out)
         switch (dg) {

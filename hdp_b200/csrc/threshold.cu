@@ -201,6 +201,7 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
     const size_t smem = (size_t)NC * b_pad * sizeof(float) + (size_t)NC * 3 * sizeof(int);
     HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((C + NC - 1) / NC), (unsigned)n_doy);
+    KernelTimer timer(kThrGeneric, st);
     k_thr_generic<<<grid, 256, smem, st>>>(x, C, T_b, ld_t, L.time_index, L.win_rows, n_doy, n_y, W, qt, P, NC, b_pad_log2, d_out);
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;

@@ -129,6 +129,19 @@ int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t
  * launched since it was loaded. */
 int64_t hdp_b200_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline: while enabled, every kernel launch is bracketed by CUDA events
+ * on its own stream.  hdp_b200_timing_read waits for the recorded launches, writes (kernel id, milliseconds)
+ * pairs in launch order (at most cap), forgets them and returns how many it wrote. */
+#define HDP_B200_KERNEL_NORMALIZE    1
+#define HDP_B200_KERNEL_THR_GENERIC  2
+#define HDP_B200_KERNEL_HOT_WORDS    3
+#define HDP_B200_KERNEL_SCAN         4
+#define HDP_B200_KERNEL_UNPACK_MASK  5
+#define HDP_B200_KERNEL_THR_SORT     6
+#define HDP_B200_KERNEL_THR_SELECT   7
+void hdp_b200_timing_enable(int on);
+int  hdp_b200_timing_read(int *ids, float *ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 // which is bit-identical to the reference (tests/test_gpu_parity.py compares at 0 ulp).
 #include <math.h>
 #include <vector>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -120,15 +121,344 @@ k_thr_generic(const float *__restrict__ temps, int64_t C, int64_t T_b, int64_t l
     }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// k_thr_ranked: the fast path.  One CTA per cell.
+//
+//   1. gather the cell's E = n_doy * n_y window elements (every slot of the reference's time_index table,
+//      -1 pads included: they are ordinary elements holding the last sample) into shared memory;
+//   2. order them ONCE with a stable LSD radix sort (4-bit digits, per-thread private counters) on the
+//      order-preserving integer image of the f32 samples, and record rank_of[element];
+//   3. every warp owns a contiguous range of days of year and keeps that window as a bitmap over RANKS
+//      (plane A: row present, plane B: row present twice - the reference's mirrored year-end wrap pools
+//      some rows twice).  Moving to the next day of year flips the bits of the rows that leave / enter;
+//   4. every requested percentile is read from that single ordering: the k-th and (k+1)-th window members
+//      are found by a popcount prefix scan across lanes and an in-word select, and interpolated in double.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kRankedThreads = 512;
+constexpr int kRankedWarps = kRankedThreads / 32;
+constexpr int kRadixBits = 4, kRadixBins = 1 << kRadixBits, kRadixPasses = 32 / kRadixBits;
+
+enum SelMode { kSelInterp = 0, kSelMax = 1, kSelMin = 2 };
+
+struct SelTable {                    // per percentile, identical for every cell and day of year (n is fixed)
+    int pos_lo[HDP_B200_MAX_PERCENTILES];     // 0-based positions in the sorted window
+    int pos_hi[HDP_B200_MAX_PERCENTILES];
+    int mode[HDP_B200_MAX_PERCENTILES];
+    double w_lo[HDP_B200_MAX_PERCENTILES];    // 1 - m
+    double w_hi[HDP_B200_MAX_PERCENTILES];    // m
+};
+
+__device__ __forceinline__ uint32_t f32_to_key(float v)
+{
+    const uint32_t u = __float_as_uint(v);
+    if (v != v) return 0xffffffffu;                               // every NaN sorts last
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float key_to_f32(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// position (0..31) of the n-th (0-based) member of the multiset {bit i of a} + {bit i of b} in rank order
+template <bool kTwoPlanes>
+__device__ __forceinline__ int select_in_word(uint32_t a, uint32_t b, int n)
+{
+    int pos = 0;
+#pragma unroll
+    for (int width = 16; width >= 1; width >>= 1) {
+        const uint32_t mask = (1u << width) - 1u;
+        int c = __popc(a & mask);
+        if (kTwoPlanes) c += __popc(b & mask);
+        if (n >= c) { n -= c; pos += width; a >>= width; if (kTwoPlanes) b >>= width; }
+    }
+    return pos;
+}
+
+// members of the window whose rank lies in [lo, hi) (warp-cooperative; non-finite bookkeeping only)
+__device__ __forceinline__ int range_count(const uint32_t *A, const uint32_t *B, bool dup, int wpl, int lane, int lo, int hi)
+{
+    int c = 0;
+    for (int i = 0; i < wpl; i++) {
+        const int w = lane * wpl + i, r0 = w * 32;
+        if (r0 + 32 <= lo || r0 >= hi) continue;
+        uint32_t m = 0xffffffffu;
+        if (lo > r0) m &= 0xffffffffu << (lo - r0);
+        if (hi < r0 + 32) m &= (1u << (hi - r0)) - 1u;
+        c += __popc(A[w] & m) + (dup ? __popc(B[w] & m) : 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+}
+
+__global__ void __launch_bounds__(kRankedThreads, 1)
+k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
+             const int *__restrict__ time_index, int E, int n_y, int n_doy, int n,
+             const int *__restrict__ op_off, const int *__restrict__ ops, const uint8_t *__restrict__ doy_dup,
+             int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out)
+{
+    constexpr int NT = kRankedThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Epad = (E + 63) & ~63;
+    uint32_t *keyA = (uint32_t *)smem_raw;                        // sorted keys after the last pass
+    uint16_t *rank_of = (uint16_t *)(keyA + Epad);                // also the second index buffer of the sort
+    uint32_t *keyB = (uint32_t *)(rank_of + Epad);
+    uint16_t *idxA = (uint16_t *)(keyB + Epad);
+    uint16_t *cnt = idxA + Epad;                                  // [16][NT] private digit counters
+    uint32_t *planes = keyB;                                      // after the sort: [warp][2][nwords_pad] (over keyB, idxA, cnt)
+    __shared__ int s_nonfinite[3];                                // NaN, +inf, -inf elements of this cell
+    __shared__ int s_warp_tot[kRankedWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t c = blockIdx.x;
+
+    if (tid < 3) s_nonfinite[tid] = 0;
+    __syncthreads();
+
+    // ---- 1. gather ----
+    const float pinf = __int_as_float(0x7f800000);
+    for (int e = tid; e < E; e += NT) {
+        int64_t t = time_index[e];
+        if (t < 0) t += T_b;                                      // -1 pads read the LAST sample (threshold.py:35,77)
+        const float v = temps[t * ld_t + c];
+        if (v != v) atomicAdd(&s_nonfinite[0], 1);
+        else if (v == pinf) atomicAdd(&s_nonfinite[1], 1);
+        else if (v == -pinf) atomicAdd(&s_nonfinite[2], 1);
+        keyA[e] = f32_to_key(v);
+        idxA[e] = (uint16_t)e;
+    }
+    __syncthreads();
+
+    // ---- 2. stable LSD radix sort of (key, element) ----
+    {
+        uint32_t *sk = keyA, *dk = keyB;
+        uint16_t *si = idxA, *di = rank_of;
+        const int e0 = min(tid * ept, E), e1 = min(e0 + ept, E);
+        for (int pass = 0; pass < kRadixPasses; pass++) {
+            const int shift = pass * kRadixBits;
+#pragma unroll
+            for (int d = 0; d < kRadixBins; d++) cnt[d * NT + tid] = 0;
+            for (int e = e0; e < e1; e++) cnt[((sk[e] >> shift) & (kRadixBins - 1)) * NT + tid]++;
+            __syncthreads();
+            // exclusive scan of the 16*NT counters in (digit, thread) order; thread t owns entries [16t, 16t+16)
+            uint16_t *mine = cnt + tid * kRadixBins;
+            int local[kRadixBins], tot = 0;
+#pragma unroll
+            for (int i = 0; i < kRadixBins; i++) { local[i] = tot; tot += mine[i]; }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            int base = incl - tot;
+            for (int w = 0; w < warp; w++) base += s_warp_tot[w];
+#pragma unroll
+            for (int i = 0; i < kRadixBins; i++) mine[i] = (uint16_t)(base + local[i]);
+            __syncthreads();
+            for (int e = e0; e < e1; e++) {
+                const uint32_t k = sk[e];
+                const int slot = ((k >> shift) & (kRadixBins - 1)) * NT + tid;
+                const int pos = cnt[slot];
+                cnt[slot] = (uint16_t)(pos + 1);
+                dk[pos] = k;
+                di[pos] = si[e];
+            }
+            __syncthreads();
+            uint32_t *tk = sk; sk = dk; dk = tk;
+            uint16_t *ti = si; si = di; di = ti;
+        }
+        // an even number of passes: sorted keys are back in keyA, their elements in idxA
+    }
+    for (int r = tid; r < E; r += NT) rank_of[idxA[r]] = (uint16_t)r;
+    __syncthreads();
+
+    // ---- 3./4. sliding rank bitmaps, one day-of-year range per warp ----
+    const int wpl = nwords_pad >> 5;                              // bitmap words per lane
+    uint32_t *A = planes + (size_t)warp * 2 * nwords_pad, *B = A + nwords_pad;
+    for (int i = lane; i < 2 * nwords_pad; i += 32) A[i] = 0u;
+    const int d_begin = warp * dpw, d_end = min(n_doy, d_begin + dpw);
+    bool range_dup = false;
+    for (int d = d_begin; d < d_end; d++) range_dup |= doy_dup[d] != 0;
+    const int n_nan = s_nonfinite[0], n_pinf = s_nonfinite[1], n_ninf = s_nonfinite[2];
+    const bool nonfinite = (n_nan | n_pinf | n_ninf) != 0;
+    __syncwarp();
+
+    for (int d = d_begin; d < d_end; d++) {
+        // rows leaving / entering the window (multiset difference to the previous day; full build on the first)
+        for (int o = op_off[d]; o < op_off[d + 1]; o++) {
+            const int op = ops[o], row = op >> 1;
+            for (int j = lane; j < n_y; j += 32) {
+                const int r = rank_of[row * n_y + j];
+                const uint32_t bit = 1u << (r & 31);
+                if (op & 1) {
+                    const uint32_t old = atomicOr(&A[r >> 5], bit);
+                    if (old & bit) atomicOr(&B[r >> 5], bit);
+                } else {
+                    if (range_dup && (B[r >> 5] & bit)) atomicAnd(&B[r >> 5], ~bit);
+                    else atomicAnd(&A[r >> 5], ~bit);
+                }
+            }
+            __syncwarp();
+        }
+        const bool dup = doy_dup[d] != 0;
+
+        // members per lane slice, inclusive scan across lanes
+        int s = 0;
+        for (int i = 0; i < wpl; i++) s += __popc(A[lane * wpl + i]);
+        if (dup) for (int i = 0; i < wpl; i++) s += __popc(B[lane * wpl + i]);
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+
+        int w_nan = 0, w_pinf = 0, w_ninf = 0;
+        if (nonfinite) {                                          // rare: count the window's non-finite members by rank range
+            w_ninf = range_count(A, B, dup, wpl, lane, 0, n_ninf);
+            w_pinf = range_count(A, B, dup, wpl, lane, E - n_nan - n_pinf, E - n_nan);
+            w_nan = range_count(A, B, dup, wpl, lane, E - n_nan, E);
+        }
+
+        for (int p0 = 0; p0 < P; p0 += 16) {
+            // lane 2i -> lower pick of percentile p0+i, lane 2i+1 -> upper pick
+            const int p = min(p0 + (lane >> 1), P - 1);
+            const int target = (lane & 1) ? sel.pos_hi[p] : sel.pos_lo[p];
+            int lo = 0, hi = 31;                                  // first lane whose inclusive count exceeds target
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi) >> 1;
+                const int v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > target) hi = mid; else lo = mid + 1;
+            }
+            const int owner = lo;
+            int rem = target - (__shfl_sync(0xffffffffu, incl, owner) - __shfl_sync(0xffffffffu, s, owner));
+            int w = owner * wpl;
+            uint32_t a = 0u, b = 0u;
+            for (int i = 0; i < wpl; i++, w++) {
+                a = A[w];
+                b = dup ? B[w] : 0u;
+                const int cw = __popc(a) + __popc(b);
+                if (rem < cw) break;
+                rem -= cw;
+            }
+            w = min(w, owner * wpl + wpl - 1);
+            const int bitpos = dup ? select_in_word<true>(a, b, rem) : select_in_word<false>(a, 0u, rem);
+            const int r = min(w * 32 + bitpos, E - 1);
+            const double val = (double)key_to_f32(keyA[r]);
+            const double lower = __shfl_sync(0xffffffffu, val, (lane & 15) * 2);
+            const double upper = __shfl_sync(0xffffffffu, val, (lane & 15) * 2 + 1);
+            if (lane < 16 && p0 + lane < P) {
+                const int pp = p0 + lane, mode = sel.mode[pp];
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                double v;
+                if (mode == kSelInterp) {                         // arraymath.py:1697-1701
+                    v = __dadd_rn(__dmul_rn(lower, sel.w_lo[pp]), __dmul_rn(upper, sel.w_hi[pp]));
+                } else if (mode == kSelMax) {                     // arraymath.py:1669-1675
+                    v = upper;
+                    if ((w_pinf | w_ninf) && isinf(v)) v = nan;
+                } else {                                          // arraymath.py:1678-1695
+                    v = lower;
+                    if (w_pinf | w_ninf) {
+                        const int n_fin = n - (w_pinf + w_ninf);
+                        if (n_fin == 0) v = nan;
+                        if (w_pinf == 1 && n == 2) v = nan;
+                        if (w_ninf > 1) v = nan;
+                        if (n_fin == 1 && w_pinf > 1 && w_ninf != 1) v = nan;
+                    }
+                }
+                if (w_nan > 0) v = nan;                           // _can_collect_percentiles, arraymath.py:1714
+                out[(c * n_doy + d) * (int64_t)P + pp] = v;
+            }
+        }
+    }
+}
+
 static bool bad_dims(int64_t C, int64_t T_b, int n_doy, int n_y, int W, int P)
 {
     return C < 0 || T_b < 0 || n_doy <= 0 || n_y <= 0 || W <= 0 || P <= 0 || T_b > 0x3fffffff;
 }
 
+// What the fast path needs besides the reference's two tables.
+struct RankedPlan {
+    bool usable = false;
+    std::vector<int> op_off, ops;       // per day of year: (row << 1 | enter) ops relative to the previous day of the warp's range
+    std::vector<uint8_t> doy_dup;       // window pools some row twice
+    int dpw = 0, ept = 0, nwords_pad = 0;
+    size_t smem = 0;
+    SelTable sel;
+};
+
+static size_t ranked_smem(int E)
+{
+    const size_t Epad = ((size_t)E + 63) & ~(size_t)63;
+    return Epad * (4 + 2 + 4 + 2) + (size_t)kRadixBins * kRankedThreads * 2;
+}
+
+static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, const double *q, int P, RankedPlan &pl)
+{
+    const int64_t E = (int64_t)n_doy * n_y, n = (int64_t)W * n_y;
+    pl.usable = false;
+    if (E > 65535 || n < 2) return;
+    pl.smem = ranked_smem((int)E);
+    if (pl.smem > 227 * 1024 - 256) return;
+    const int nwords = (int)((E + 31) / 32);
+    pl.nwords_pad = (nwords + 31) / 32 * 32;
+    if ((size_t)kRankedWarps * 2 * pl.nwords_pad * 4 > pl.smem - (((size_t)E + 63) & ~(size_t)63) * 6) return;
+    pl.dpw = (n_doy + kRankedWarps - 1) / kRankedWarps;
+    pl.ept = (int)((E + kRankedThreads - 1) / kRankedThreads) | 1;          // odd: conflict-free strided key reads
+    pl.doy_dup.assign(n_doy, 0);
+    pl.op_off.assign(n_doy + 1, 0);
+    pl.ops.clear();
+    std::vector<int> cur(n_doy), prev(n_doy);
+    for (int d = 0; d < n_doy; d++) {
+        std::fill(cur.begin(), cur.end(), 0);
+        for (int k = 0; k < W; k++) cur[win_rows[d * W + k]]++;
+        for (int r = 0; r < n_doy; r++) {
+            if (cur[r] > 2) return;                                         // more than twice: generic kernel
+            if (cur[r] == 2) pl.doy_dup[d] = 1;
+        }
+        const bool first = d % pl.dpw == 0;
+        pl.op_off[d] = (int)pl.ops.size();
+        for (int r = 0; r < n_doy; r++) {
+            const int before = first ? 0 : prev[r];
+            for (int i = cur[r]; i < before; i++) pl.ops.push_back(r << 1);        // leaves first ...
+        }
+        for (int r = 0; r < n_doy; r++) {
+            const int before = first ? 0 : prev[r];
+            for (int i = before; i < cur[r]; i++) pl.ops.push_back((r << 1) | 1);  // ... then enters
+        }
+        prev.swap(cur);
+    }
+    pl.op_off[n_doy] = (int)pl.ops.size();
+    // positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
+    for (int p = 0; p < HDP_B200_MAX_PERCENTILES; p++) {
+        pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = 0;
+        pl.sel.mode[p] = kSelInterp;
+        pl.sel.w_lo[p] = pl.sel.w_hi[p] = 0.0;
+        if (p >= P) continue;
+        volatile double pct = q[p] * 100.0;
+        if (pct == 100.0) { pl.sel.mode[p] = kSelMax; pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = (int)n - 1; continue; }
+        if (pct == 0.0) { pl.sel.mode[p] = kSelMin; continue; }
+        volatile double frac = pct / 100.0;
+        volatile double scaled = (double)(n - 1) * frac;
+        volatile double rank = 1.0 + scaled;
+        const double f = floor(rank);
+        volatile double m = rank - f;
+        volatile double w0 = 1.0 - m;
+        int64_t k = (int64_t)f - 1;
+        if (k < 0) k = 0;
+        if (k >= n - 1) { pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = (int)n - 1; }
+        else { pl.sel.pos_lo[p] = (int)k; pl.sel.pos_hi[p] = (int)k + 1; }
+        pl.sel.w_lo[p] = w0;
+        pl.sel.w_hi[p] = m;
+    }
+    pl.usable = true;
+}
+
 struct ThrLayout {
     size_t total = 0;
     float *xn = nullptr;
-    int *time_index = nullptr, *win_rows = nullptr;
+    int *time_index = nullptr, *win_rows = nullptr, *op_off = nullptr, *ops = nullptr;
+    uint8_t *doy_dup = nullptr;
 };
 
 static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_norm, int n_doy, int n_y, int W)
@@ -138,15 +468,22 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     if (need_norm) L.xn = cv.take<float>((size_t)C * T_b);
     L.time_index = cv.take<int>((size_t)n_doy * n_y);
     L.win_rows = cv.take<int>((size_t)n_doy * W);
+    L.op_off = cv.take<int>((size_t)n_doy + 1);
+    L.ops = cv.take<int>((size_t)2 * W * (n_doy + kRankedWarps));           // <= 2W changes per day, W per range start
+    L.doy_dup = cv.take<uint8_t>((size_t)n_doy);
     L.total = cv.off;
     return L;
 }
+
+static int g_force_generic = 0;
 
 }  // namespace hdp
 
 using namespace hdp;
 
 extern "C" {
+
+void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on; }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                                            int n_doy, int n_y, int W, int P)
@@ -190,8 +527,24 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
         ld_t = C;
     }
     HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.win_rows, h_win_rows, sizeof(int) * (size_t)n_doy * W, cudaMemcpyHostToDevice, st));
 
+    RankedPlan plan;
+    if (!g_force_generic) plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, plan);
+    if (plan.usable) {
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.op_off, plan.op_off.data(), sizeof(int) * plan.op_off.size(), cudaMemcpyHostToDevice, st));
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_dup, plan.doy_dup.data(), plan.doy_dup.size(), cudaMemcpyHostToDevice, st));
+        HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        KernelTimer timer(kThrSort, st);
+        k_thr_ranked<<<(unsigned)C, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
+                                                                    L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
+                                                                    plan.sel, P, d_out);
+        HDP_LAUNCH_CHECK();
+        return HDP_B200_OK;
+    }
+
+    // generic path: any table, any multiplicity
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.win_rows, h_win_rows, sizeof(int) * (size_t)n_doy * W, cudaMemcpyHostToDevice, st));
     int b_pad_log2 = 1;
     while ((1 << b_pad_log2) < b) b_pad_log2++;
     const int b_pad = 1 << b_pad_log2;

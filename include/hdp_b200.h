@@ -77,6 +77,10 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
                         double *d_out,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Test hook: route every hdp_b200_thresholds call through the generic gather+sort kernel (the path used for
+ * tables the ranked kernel does not cover: rows pooled more than twice, windows that do not fit shared memory). */
+void hdp_b200_thresholds_force_generic(int on);
+
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                              const double *h_q, int P,

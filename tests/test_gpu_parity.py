@@ -32,8 +32,17 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
+@pytest.fixture(params=["ranked", "generic"])
+def thr_path(request, core):
+    """Both threshold kernels: the ranked fast path and the generic gather+sort fallback."""
+    from hdp_b200 import _lib
+    _lib.lib().hdp_b200_thresholds_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    _lib.lib().hdp_b200_thresholds_force_generic(0)
+
+
 @pytest.mark.parametrize("name", ["noleap6_r7", "std9_r15", "d360_r2", "noleap3_r0", "noleap30_r7", "special_r3"])
-def test_thresholds_golden(core, golden_percentiles, name):
+def test_thresholds_golden(core, golden_percentiles, name, thr_path):
     from hdp_b200 import _tables as tb
     g = golden_percentiles
     wt = tb.window_tables(g[f"{name}.dayofyr"], int(g[f"{name}.radius"]))
@@ -53,7 +62,7 @@ def test_thresholds_layouts_and_host(core, golden_percentiles):
     assert bits_equal(core.thresholds_host(np.ascontiguousarray(x.T).T, wt, q), want)
 
 
-def test_thresholds_random_vs_oracle(core):
+def test_thresholds_random_vs_oracle(core, thr_path):
     from hdp_b200 import _tables as tb
     rng = np.random.default_rng(7)
     ax = tb.TimeAxis.daily((1961, 1, 1), 5 * 365, "noleap")
@@ -61,10 +70,27 @@ def test_thresholds_random_vs_oracle(core):
     C = 203                                                   # ragged: not a multiple of any tile
     x = (15 + 10 * np.sin(2 * np.pi * ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(ax), C))).astype(np.float32)
     x[rng.integers(0, len(ax), 20), rng.integers(0, C, 20)] = np.nan
+    x[rng.integers(0, len(ax), 20), rng.integers(0, C, 20)] = np.inf
+    x[rng.integers(0, len(ax), 20), rng.integers(0, C, 20)] = -np.inf
+    x[:, 5] = np.round(x[:, 5])                               # heavy ties
+    x[:, 6] = 1.5                                             # constant series
     q = np.array([0.0, 0.1, 0.5, 0.9, 0.95, 0.999, 1.0])
     want = oracle.thresholds_batch(x, wt.window_samples(), q)
     got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
     assert bits_equal(got, want)
+
+
+def test_thresholds_many_percentiles_and_leap(core, thr_path):
+    # 20 percentiles (two select rounds), leap calendar with -1 pads and a 31-day window (ERA5-like shape)
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(17)
+    ax = tb.TimeAxis.date_range("1991-01-01", "2000-12-31", "standard")
+    wt = tb.window_tables(ax.dayofyr, 15)
+    assert (wt.time_index < 0).any()
+    x = (10 * np.sin(2 * np.pi * ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(ax), 37))).astype(np.float32)
+    q = np.linspace(0.80, 0.99, 20)
+    want = oracle.thresholds_batch(x, wt.window_samples(), q)
+    assert bits_equal(core.thresholds_array(dev(x), wt, q).cpu().numpy(), want)
 
 
 def test_thresholds_errors(core):

@@ -26,11 +26,6 @@
 
 namespace hdp {
 
-struct DefTable {
-    int min_dur[HDP_B200_MAX_DEFINITIONS];
-    int max_break[HDP_B200_MAX_DEFINITIONS];
-    int max_subs[HDP_B200_MAX_DEFINITIONS];
-};
 
 // ----------------------------------------------------------------------------------------------------
 // k_hot_words
@@ -113,30 +108,51 @@ k_unpack_mask(const uint32_t *__restrict__ hot, int64_t C, int64_t T, int P, int
 // ----------------------------------------------------------------------------------------------------
 // k_scan
 // ----------------------------------------------------------------------------------------------------
+// One thread per (cell, percentile); lanes = 32 neighbouring cells.  Every definition's state machine
+// (reference index_heatwaves, hdp/metric.py:39-58) is advanced BIT-PARALLEL: bit i of each state word
+// belongs to definition i, so one hot run costs the same ~25 logic instructions for 1 or 32 definitions.
+//   inhw        bit i = in_heatwave of definition i
+//   rem[k]      bit-sliced down counter: remaining subsequent events = max_subs - sub_events
+//   fresh       bit i = the next labelled run of definition i starts a heatwave id not yet seen in the open season
+// Lanes pop their own events (each lane advances through its hot words at its own pace), so the warp
+// stays converged on the event body instead of idling behind the busiest cell.
+// Season accumulators are packed two definitions per register (16-bit halves): cnt (days of the current
+// id in the open season), HWF, HWN, HWD.
+//
 // Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
 // (the host splits overlapping tables into several passes, one launch each).
-template <int DG>
+struct ScanTables {
+    uint32_t max_subs_plane[32];     // bit k of max_subs of every definition (bit-sliced constants)
+    int ge_len, brk_len;             // table lengths: max(min_dur) + 2, max(max_break) + 2
+};
+
+template <int NP, int KS>
 __global__ void __launch_bounds__(256)
 k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
-       int P, int D, const __grid_constant__ DefTable defs,
+       int P, int D, const __grid_constant__ ScanTables tabs, const uint32_t *__restrict__ ge_tab, const uint32_t *__restrict__ brk_tab,
        const int4 *__restrict__ seasons_north, int n_north, const int4 *__restrict__ seasons_south, int n_south, int Y,
        const uint8_t *__restrict__ is_south, uint16_t *__restrict__ out)
 {
+    extern __shared__ uint32_t smem_scan[];
+    uint4 *lut8 = (uint4 *)smem_scan;                             // [256]: byte of definition bits -> 4 pair selectors
+    uint32_t *ge_s = smem_scan + 256 * 4;                         // [ge_len]  definitions with min_dur <= len
+    uint32_t *brk_s = ge_s + tabs.ge_len;                         // [brk_len] definitions with max_break < gap
+    const int tid = threadIdx.y * 32 + threadIdx.x, nthreads = blockDim.y * 32;
+    for (int b = tid; b < 256; b += nthreads) {
+        uint4 v;
+        v.x = (b & 1) | ((b >> 1 & 1) << 16);
+        v.y = (b >> 2 & 1) | ((b >> 3 & 1) << 16);
+        v.z = (b >> 4 & 1) | ((b >> 5 & 1) << 16);
+        v.w = (b >> 6 & 1) | ((b >> 7 & 1) << 16);
+        lut8[b] = v;
+    }
+    for (int i = tid; i < tabs.ge_len; i += nthreads) ge_s[i] = ge_tab[i];
+    for (int i = tid; i < tabs.brk_len; i += nthreads) brk_s[i] = brk_tab[i];
+    __syncthreads();
+
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int p = blockIdx.y * blockDim.y + threadIdx.y;
-    const int d0 = blockIdx.z * DG;
     if (c >= C || p >= P) return;
-
-    int min_dur[DG], max_break[DG], max_subs[DG];
-    int least_min_dur = INT_MAX;
-#pragma unroll
-    for (int i = 0; i < DG; i++) {
-        const bool live = d0 + i < D;
-        min_dur[i] = live ? defs.min_dur[d0 + i] : INT_MAX;      // padding definitions never label a run
-        max_break[i] = live ? defs.max_break[d0 + i] : INT_MAX;
-        max_subs[i] = live ? defs.max_subs[d0 + i] : 0;
-        least_min_dur = min(least_min_dur, min_dur[i]);
-    }
 
     const bool south = is_south != nullptr && is_south[c] != 0;
     const int4 *seas = south ? seasons_south : seasons_north;
@@ -145,26 +161,33 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     int a_cur = INT_MAX, b_cur = INT_MAX, row_cur = 0;
     if (n_seasons > 0) { const int4 s4 = seas[0]; a_cur = s4.x; b_cur = s4.y; row_cur = s4.z; }
 
-    // per-definition state (registers): reference's in_heatwave / sub_events (metric.py:34-36), and the open
-    // season's accumulators.  cnt = days carrying the current heatwave id inside the open season.
-    uint32_t inhw = 0u;
-    int sub[DG], cnt[DG], hwf[DG], hwn[DG], hwd[DG];
+    uint32_t inhw = 0u, sublt = 0u, fresh = 0xffffffffu;
+    uint32_t rem[KS];
 #pragma unroll
-    for (int i = 0; i < DG; i++) { sub[i] = 0; cnt[i] = 0; hwf[i] = 0; hwn[i] = 0; hwd[i] = 0; }
+    for (int k = 0; k < KS; k++) { rem[k] = tabs.max_subs_plane[k]; sublt |= rem[k]; }     // sub_events = 0
+    uint32_t cnt2[NP], hwf2[NP], hwn2[NP], hwd2[NP];              // definitions 2j (low half) and 2j+1 (high half)
+#pragma unroll
+    for (int j = 0; j < NP; j++) { cnt2[j] = 0u; hwf2[j] = 0u; hwn2[j] = 0u; hwd2[j] = 0u; }
 
     const int64_t plane = (int64_t)P * D * Y * C;                 // one metric
     auto flush = [&]() {                                          // close season `ys`
 #pragma unroll
-        for (int i = 0; i < DG; i++) {
-            if (d0 + i < D) {
-                const int64_t o = (((int64_t)p * D + (d0 + i)) * Y + row_cur) * C + c;
-                out[o] = (uint16_t)hwf[i];
-                out[o + plane] = (uint16_t)hwn[i];
-                out[o + 2 * plane] = (uint16_t)hwd[i];
-                out[o + 3 * plane] = (uint16_t)(hwn[i] > 0 ? hwf[i] / hwn[i] : 0);   // trunc(mean), metric.py:340
+        for (int j = 0; j < NP; j++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int d = 2 * j + h;
+                if (d < D) {
+                    const uint32_t f = (hwf2[j] >> (16 * h)) & 0xffffu, nn = (hwn2[j] >> (16 * h)) & 0xffffu;
+                    const int64_t o = (((int64_t)p * D + d) * Y + row_cur) * C + c;
+                    out[o] = (uint16_t)f;
+                    out[o + plane] = (uint16_t)nn;
+                    out[o + 2 * plane] = (uint16_t)(hwd2[j] >> (16 * h));
+                    out[o + 3 * plane] = (uint16_t)(nn ? f / nn : 0u);       // trunc(mean), metric.py:340
+                }
             }
-            cnt[i] = 0; hwf[i] = 0; hwn[i] = 0; hwd[i] = 0;
+            cnt2[j] = 0u; hwf2[j] = 0u; hwn2[j] = 0u; hwd2[j] = 0u;
         }
+        fresh = 0xffffffffu;
         ys++;
         if (ys < n_seasons) { const int4 s4 = seas[ys]; a_cur = s4.x; b_cur = s4.y; row_cur = s4.z; }
         else { a_cur = INT_MAX; b_cur = INT_MAX; }
@@ -173,68 +196,87 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     int prev_e = -(1 << 29);      // end of the previous hot run
     int run_start = -1;           // start of the hot run still open at the end of the previous word
     const uint32_t *hp = hot + (int64_t)p * K * C + c;
+    const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
 
+    int k = -1, t0 = 0;
+    uint32_t starts = 0u, ends = 0u;
     uint32_t m_next = K > 0 ? hp[0] : 0u;
-    for (int k = 0; k <= K; k++) {
-        // word K is a virtual cold day at t = T that closes a run reaching the end of the series
-        const uint32_t m = m_next;
-        int t0 = T, nb = 1;
-        if (k < K) { const int4 w = words[k]; t0 = w.x; nb = w.y; }
-        m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
-
-        const uint32_t carry = run_start >= 0 ? 1u : 0u;
-        const uint32_t prev = (m << 1) | carry;                   // bit i = day i-1 hot
-        uint32_t starts = m & ~prev;
-        uint32_t ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-        while (ends) {
-            const int e = t0 + __ffs(ends) - 1;
-            ends &= ends - 1;
-            int s = run_start;
-            if (s < 0) { s = t0 + __ffs(starts) - 1; starts &= starts - 1; }
-            run_start = -1;
-
-            // ---- one hot run [s, e): reference index_heatwaves branches A-D, metric.py:39-58 ----
-            const int len = e - s, gap = s - prev_e;
-            prev_e = e;
-            if (inhw == 0u && len < least_min_dur) continue;      // no definition can react
-            uint32_t lab = 0u;
-#pragma unroll
-            for (int i = 0; i < DG; i++) {
-                const uint32_t bit = 1u << i;
-                if (gap > max_break[i]) inhw &= ~bit;             // B: the break before this run was too long
-                const bool ge = len >= min_dur[i];
-                if (!(inhw & bit)) {                              // A: a new heatwave starts (or nothing happens)
-                    if (ge) { inhw |= bit; lab |= bit; cnt[i] = 0; }
-                } else if (sub[i] < max_subs[i]) {                // C: subsequent event of the current heatwave
-                    sub[i]++;
-                    lab |= bit;
-                } else {                                          // D: subsequent events used up
-                    if (ge) { lab |= bit; cnt[i] = 0; }
-                    else inhw &= ~bit;
-                    sub[i] = 0;
-                }
+    for (;;) {
+        // ---- refill: advance through hot words until this lane has a run end to process ----
+        while (ends == 0u) {
+            if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }    // at most one start is left: the run stays open
+            k++;
+            if (k > K) break;
+            uint32_t m = 0u;
+            int nb = 1;
+            t0 = T;                                               // word K is a virtual cold day closing a run at the series end
+            if (k < K) {
+                const int4 w = words[k];
+                m = m_next; t0 = w.x; nb = w.y;
+                m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
             }
-            if (lab == 0u) continue;
-            // ---- season accounting: HWF / HWN / HWD (metric.py:63-137) over [s, e) ----
-            while (b_cur <= s) flush();
-            while (a_cur < e) {
-                const int days = min(e, b_cur) - max(s, a_cur);
-                if (days > 0) {
+            const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);       // bit i = day i-1 hot
+            starts = m & ~prev;
+            ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        }
+        if (ends == 0u) break;
+
+        // ---- one hot run [s, e) ----
+        const int e = t0 + __ffs(ends) - 1;
+        ends &= ends - 1;
+        int s = run_start;
+        if (s < 0) { s = t0 + __ffs(starts) - 1; starts &= starts - 1; }
+        run_start = -1;
+        const int len = e - s, gap = s - prev_e;
+        prev_e = e;
+
+        // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
+        const uint32_t ge = ge_s[min(len, ge_cap)];               // len >= min_duration
+        inhw &= ~brk_s[min(gap, brk_cap)];                        // B: the break before this run was too long
+        const uint32_t A = ~inhw & ge;                            // A: a new heatwave starts
+        const uint32_t Cm = inhw & sublt;                         // C: subsequent event of the current heatwave
+        const uint32_t Dm = inhw & ~sublt;                        // D: subsequent events used up
+        const uint32_t Dn = Dm & ge;                              //    ... long enough: new heatwave id
+        const uint32_t lab = A | Cm | Dn;
+        fresh |= A | Dn;
+        inhw = (inhw | A) & ~(Dm & ~ge);
+        uint32_t borrow = Cm;
+        sublt = 0u;
 #pragma unroll
-                    for (int i = 0; i < DG; i++) {
-                        if (lab & (1u << i)) {
-                            hwn[i] += (cnt[i] == 0);
-                            cnt[i] += days;
-                            hwf[i] += days;
-                            hwd[i] = max(hwd[i], cnt[i]);
+        for (int q = 0; q < KS; q++) {                            // rem -= 1 where C, rem = max_subs where D
+            const uint32_t t = ~rem[q] & borrow;
+            rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
+            borrow = t;
+            sublt |= rem[q];
+        }
+        if (lab == 0u) continue;
+
+        // ---- season accounting: HWF / HWN / HWD (metric.py:63-137) over [s, e) ----
+        while (b_cur <= s) flush();
+        while (a_cur < e) {
+            const uint32_t days = (uint32_t)max(min(e, b_cur) - max(s, a_cur), 0);
+            if (days > 0u) {
+                const uint32_t newly = lab & fresh;               // first labelled run of an id inside this season
+                fresh &= ~lab;
+#pragma unroll
+                for (int j0 = 0; j0 < NP; j0 += 4) {
+                    const uint4 sl = lut8[(lab >> (2 * j0)) & 255u], sn = lut8[(newly >> (2 * j0)) & 255u];
+                    const uint32_t sel[4] = {sl.x, sl.y, sl.z, sl.w}, neu[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (j0 + q < NP) {
+                            const int j = j0 + q;
+                            cnt2[j] = (cnt2[j] & ~(neu[q] * 0xffffu)) + days * sel[q];
+                            hwf2[j] += days * sel[q];
+                            hwn2[j] += neu[q];
+                            hwd2[j] = __vmaxu2(hwd2[j], cnt2[j]);
                         }
                     }
                 }
-                if (e <= b_cur) break;
-                flush();
             }
+            if (e <= b_cur) break;
+            flush();
         }
-        if (starts) run_start = t0 + __ffs(starts) - 1;           // at most one start is left: the run stays open
     }
     while (ys < n_seasons) flush();
 }
@@ -312,23 +354,13 @@ static int pick_pg(int P)
     return best;
 }
 
-static int pick_dg(int D)
-{
-    const int cand[] = {2, 4, 6, 8};
-    int best = 2, best_waste = INT_MAX;
-    for (int dg : cand) {
-        const int waste = (D + dg - 1) / dg * dg - D;
-        if (waste < best_waste || (waste == best_waste && dg > best)) { best = dg; best_waste = waste; }
-    }
-    return best;
-}
-
 struct Layout {
     size_t total = 0;
     float *xn = nullptr;
     int4 *words = nullptr;
     int *blk_start = nullptr, *blk_words = nullptr;
     int4 *seasons = nullptr;
+    uint32_t *lut = nullptr;
     uint32_t *hot = nullptr;
 };
 
@@ -341,6 +373,7 @@ static Layout carve(void *ws, size_t ws_bytes, int64_t C, int64_t T, bool need_n
     L.blk_start = cv.take<int>((size_t)(n_doy + kTileDoy - 1) / kTileDoy + 1);
     L.blk_words = cv.take<int>((size_t)K + 1);
     L.seasons = cv.take<int4>((size_t)2 * (Y + 1));
+    L.lut = cv.take<uint32_t>((size_t)2 * 8192);
     L.hot = cv.take<uint32_t>((size_t)P * K * C);
     L.total = cv.off;
     return L;
@@ -485,16 +518,39 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
     if (rc != HDP_B200_OK || C == 0 || Y == 0) return rc;
     const int K = (int)plan.words.size();
 
-    DefTable defs;
-    for (int i = 0; i < HDP_B200_MAX_DEFINITIONS; i++) {
-        defs.min_dur[i] = i < D ? h_defs[3 * i] : INT_MAX;
-        defs.max_break[i] = i < D ? h_defs[3 * i + 1] : INT_MAX;
-        defs.max_subs[i] = i < D ? h_defs[3 * i + 2] : 0;
+    // bit-sliced definition tables (see k_scan)
+    ScanTables tabs;
+    int max_min_dur = 0, max_break_all = 0;
+    int64_t max_subs_all = 0;
+    std::vector<int64_t> subs(D);
+    for (int i = 0; i < D; i++) {
+        max_min_dur = std::max(max_min_dur, h_defs[3 * i]);
+        max_break_all = std::max(max_break_all, h_defs[3 * i + 1]);
+        subs[i] = std::min<int64_t>(std::max<int64_t>(h_defs[3 * i + 2], 0), T);   // more subsequent events than days cannot happen
+        max_subs_all = std::max(max_subs_all, subs[i]);
     }
-    const int dg = pick_dg(D);
+    if (max_min_dur > 8190 || max_break_all > 8190) return HDP_B200_ERR_UNSUPPORTED;
+    tabs.ge_len = max_min_dur + 2;
+    tabs.brk_len = max_break_all + 2;
+    int ks_needed = 1;
+    while ((max_subs_all >> ks_needed) != 0) ks_needed++;
+    for (int k = 0; k < 32; k++) {
+        tabs.max_subs_plane[k] = 0u;
+        for (int i = 0; i < D; i++) tabs.max_subs_plane[k] |= (uint32_t)((subs[i] >> k) & 1) << i;
+    }
+    std::vector<uint32_t> lut(tabs.ge_len + tabs.brk_len, 0u);
+    for (int l = 0; l < tabs.ge_len; l++)
+        for (int i = 0; i < D; i++) if (h_defs[3 * i] <= l) lut[l] |= 1u << i;
+    for (int g = 0; g < tabs.brk_len; g++)
+        for (int i = 0; i < D; i++) if (h_defs[3 * i + 1] < g) lut[tabs.ge_len + g] |= 1u << i;
+    HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
+    const uint32_t *ge_tab = L.lut, *brk_tab = L.lut + tabs.ge_len;
+    const size_t scan_smem = (256 * 4 + lut.size()) * sizeof(uint32_t);
     const int pw = std::min(P, 8);
     dim3 block(32, pw);
-    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((P + pw - 1) / pw), (unsigned)((D + dg - 1) / dg));
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((P + pw - 1) / pw));
+    const int np = D <= 6 ? 3 : D <= 8 ? 4 : D <= 16 ? 8 : D <= 24 ? 12 : 16;
+    const int ks = ks_needed <= 1 ? 1 : ks_needed <= 2 ? 2 : ks_needed <= 4 ? 4 : ks_needed <= 16 ? 16 : 32;
 
     // all passes of both hemispheres live side by side in the workspace: north passes, then south passes
     std::vector<int4> tab;
@@ -511,14 +567,25 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         const int nn = ip < passes[0].size() ? (int)passes[0][ip].size() : 0;
         const int ns = ip < passes[1].size() ? (int)passes[1][ip].size() : 0;
         KernelTimer timer(kScan, st);
-#define HDP_LAUNCH_SCAN(DG) \
-        k_scan<DG><<<grid, block, 0, st>>>(L.hot, C, K, (int)T, L.words, P, D, defs, sn, nn, ss, ns, Y, d_is_south, d_out)
-        switch (dg) {
-        case 2: HDP_LAUNCH_SCAN(2); break;
-        case 4: HDP_LAUNCH_SCAN(4); break;
-        case 6: HDP_LAUNCH_SCAN(6); break;
-        default: HDP_LAUNCH_SCAN(8); break;
+#define HDP_LAUNCH_SCAN(NP, KS)                                                                                          \
+        k_scan<NP, KS><<<grid, block, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, sn, nn, ss, ns, \
+                                                       Y, d_is_south, d_out)
+#define HDP_SCAN_KS(NP)                                                    \
+        switch (ks) {                                                      \
+        case 1: HDP_LAUNCH_SCAN(NP, 1); break;                             \
+        case 2: HDP_LAUNCH_SCAN(NP, 2); break;                             \
+        case 4: HDP_LAUNCH_SCAN(NP, 4); break;                             \
+        case 16: HDP_LAUNCH_SCAN(NP, 16); break;                           \
+        default: HDP_LAUNCH_SCAN(NP, 32); break;                           \
         }
+        switch (np) {
+        case 3: HDP_SCAN_KS(3); break;
+        case 4: HDP_SCAN_KS(4); break;
+        case 8: HDP_SCAN_KS(8); break;
+        case 12: HDP_SCAN_KS(12); break;
+        default: HDP_SCAN_KS(16); break;
+        }
+#undef HDP_SCAN_KS
 #undef HDP_LAUNCH_SCAN
         HDP_LAUNCH_CHECK();
     }

@@ -226,6 +226,21 @@ def test_metrics_random_sweep_vs_oracle(core):
     assert np.array_equal(hwa, np.where(hwn > 0, hwf // np.maximum(hwn, 1), 0))
 
 
+@pytest.mark.parametrize("D", [1, 2, 7, 8, 9, 17, 25, 32])
+def test_metrics_definition_counts_and_ranges(core, D):
+    # every kernel instantiation (definition pairs x sub-event counter planes), incl. large max_subs / min_duration
+    rng = np.random.default_rng(100 + D)
+    T, C = 1500, 70
+    masks = rng.random((T, C)) < rng.uniform(0.2, 0.8, C)[None, :]
+    big = [1, 3, 9, 200, 5000][D % 5]
+    defs = np.stack([rng.integers(0, 9, D), rng.integers(0, 4, D), rng.integers(0, big + 1, D)], axis=1)
+    defs[0] = [40, 0, 0] if D > 1 else defs[0]
+    defs[-1] = [2, 30, big]
+    seasons_n = [[i * 250 + 20, i * 250 + 170] for i in range(6)]
+    seasons_s = [[i * 250 + 150, i * 250 + 260] for i in range(6)]
+    _mask_case(core, masks, defs.tolist(), seasons_n, seasons_s, rng.integers(0, 2, C))
+
+
 def test_metrics_tiny_and_empty(core):
     one = _mask_case(core, [[1]], [[1, 0, 0], [2, 0, 0]], [[0, 1]], [[0, 1]], None)
     assert one[0, :, 0, 0, 0].tolist() == [1, 0]

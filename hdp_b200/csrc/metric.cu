@@ -137,6 +137,7 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     uint4 *lut8 = (uint4 *)smem_scan;                             // [256]: byte of definition bits -> 4 pair selectors
     uint32_t *ge_s = smem_scan + 256 * 4;                         // [ge_len]  definitions with min_dur <= len
     uint32_t *brk_s = ge_s + tabs.ge_len;                         // [brk_len] definitions with max_break < gap
+    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 1] first day of every hot word (last = T)
     const int tid = threadIdx.y * 32 + threadIdx.x, nthreads = blockDim.y * 32;
     for (int b = tid; b < 256; b += nthreads) {
         uint4 v;
@@ -148,6 +149,7 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     }
     for (int i = tid; i < tabs.ge_len; i += nthreads) ge_s[i] = ge_tab[i];
     for (int i = tid; i < tabs.brk_len; i += nthreads) brk_s[i] = brk_tab[i];
+    for (int i = tid; i <= K; i += nthreads) word_t0[i] = i < K ? words[i].x : T;
     __syncthreads();
 
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -198,87 +200,97 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     const uint32_t *hp = hot + (int64_t)p * K * C + c;
     const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
 
+    // accounting of `days` heatwave days of the definitions in `lab` to the open season (HWF/HWN/HWD, metric.py:63-137)
+    auto account = [&](uint32_t lab, uint32_t days) {
+        const uint32_t newly = lab & fresh;                       // first labelled run of an id inside this season
+        fresh &= ~lab;
+#pragma unroll
+        for (int j0 = 0; j0 < NP; j0 += 4) {
+            const uint4 sl = lut8[(lab >> (2 * j0)) & 255u], sn = lut8[(newly >> (2 * j0)) & 255u];
+            const uint32_t sel[4] = {sl.x, sl.y, sl.z, sl.w}, neu[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (j0 + q < NP) {
+                    const int j = j0 + q;
+                    cnt2[j] = (cnt2[j] & ~(neu[q] * 0xffffu)) + days * sel[q];
+                    hwf2[j] += days * sel[q];
+                    hwn2[j] += neu[q];
+                    hwd2[j] = __vmaxu2(hwd2[j], cnt2[j]);
+                }
+            }
+        }
+    };
+
     int k = -1, t0 = 0;
     uint32_t starts = 0u, ends = 0u;
     uint32_t m_next = K > 0 ? hp[0] : 0u;
-    for (;;) {
-        // ---- refill: advance through hot words until this lane has a run end to process ----
-        while (ends == 0u) {
-            if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }    // at most one start is left: the run stays open
-            k++;
-            if (k > K) break;
-            uint32_t m = 0u;
-            int nb = 1;
-            t0 = T;                                               // word K is a virtual cold day closing a run at the series end
-            if (k < K) {
-                const int4 w = words[k];
-                m = m_next; t0 = w.x; nb = w.y;
-                m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
-            }
-            const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);       // bit i = day i-1 hot
-            starts = m & ~prev;
-            ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+    uint32_t pend_lab = 0u;       // labelled run that continues past the end of the season being closed
+    int pend_s = 0, pend_e = 0;
+
+    // One iteration per season of this lane's table: consume (lane-asynchronously) every run that starts
+    // before the season ends, then close the season with the whole warp converged on the stores.
+    for (; ys < n_seasons;) {
+        if (pend_lab) {
+            const int days = min(pend_e, b_cur) - max(pend_s, a_cur);
+            if (days > 0) account(pend_lab, (uint32_t)days);
+            if (pend_e <= b_cur) pend_lab = 0u;
         }
-        if (ends == 0u) break;
-
-        // ---- one hot run [s, e) ----
-        const int e = t0 + __ffs(ends) - 1;
-        ends &= ends - 1;
-        int s = run_start;
-        if (s < 0) { s = t0 + __ffs(starts) - 1; starts &= starts - 1; }
-        run_start = -1;
-        const int len = e - s, gap = s - prev_e;
-        prev_e = e;
-
-        // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
-        const uint32_t ge = ge_s[min(len, ge_cap)];               // len >= min_duration
-        inhw &= ~brk_s[min(gap, brk_cap)];                        // B: the break before this run was too long
-        const uint32_t A = ~inhw & ge;                            // A: a new heatwave starts
-        const uint32_t Cm = inhw & sublt;                         // C: subsequent event of the current heatwave
-        const uint32_t Dm = inhw & ~sublt;                        // D: subsequent events used up
-        const uint32_t Dn = Dm & ge;                              //    ... long enough: new heatwave id
-        const uint32_t lab = A | Cm | Dn;
-        fresh |= A | Dn;
-        inhw = (inhw | A) & ~(Dm & ~ge);
-        uint32_t borrow = Cm;
-        sublt = 0u;
-#pragma unroll
-        for (int q = 0; q < KS; q++) {                            // rem -= 1 where C, rem = max_subs where D
-            const uint32_t t = ~rem[q] & borrow;
-            rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
-            borrow = t;
-            sublt |= rem[q];
-        }
-        if (lab == 0u) continue;
-
-        // ---- season accounting: HWF / HWN / HWD (metric.py:63-137) over [s, e) ----
-        while (b_cur <= s) flush();
-        while (a_cur < e) {
-            const uint32_t days = (uint32_t)max(min(e, b_cur) - max(s, a_cur), 0);
-            if (days > 0u) {
-                const uint32_t newly = lab & fresh;               // first labelled run of an id inside this season
-                fresh &= ~lab;
-#pragma unroll
-                for (int j0 = 0; j0 < NP; j0 += 4) {
-                    const uint4 sl = lut8[(lab >> (2 * j0)) & 255u], sn = lut8[(newly >> (2 * j0)) & 255u];
-                    const uint32_t sel[4] = {sl.x, sl.y, sl.z, sl.w}, neu[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (j0 + q < NP) {
-                            const int j = j0 + q;
-                            cnt2[j] = (cnt2[j] & ~(neu[q] * 0xffffu)) + days * sel[q];
-                            hwf2[j] += days * sel[q];
-                            hwn2[j] += neu[q];
-                            hwd2[j] = __vmaxu2(hwd2[j], cnt2[j]);
-                        }
-                    }
+        while (pend_lab == 0u) {
+            // ---- refill: advance through hot words until this lane has a run end to process ----
+            while (ends == 0u) {
+                if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }   // at most one start is left: the run stays open
+                k++;
+                if (k > K) break;
+                uint32_t m = 0u;
+                int nb = 1;
+                t0 = T;                                           // word K is a virtual cold day closing a run at the series end
+                if (k < K) {
+                    t0 = word_t0[k];
+                    nb = word_t0[k + 1] - t0;
+                    m = m_next;
+                    m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
                 }
+                const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);   // bit i = day i-1 hot
+                starts = m & ~prev;
+                ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
             }
-            if (e <= b_cur) break;
-            flush();
+            if (ends == 0u) break;                                // series exhausted
+            // ---- next hot run [s, e): leave it queued if it starts after this season ----
+            const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
+            if (s >= b_cur) break;
+            const int e = t0 + __ffs(ends) - 1;
+            ends &= ends - 1;
+            if (run_start >= 0) run_start = -1; else starts &= starts - 1;
+            const int len = e - s, gap = s - prev_e;
+            prev_e = e;
+
+            // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
+            const uint32_t ge = ge_s[min(len, ge_cap)];           // len >= min_duration
+            inhw &= ~brk_s[min(gap, brk_cap)];                    // B: the break before this run was too long
+            const uint32_t A = ~inhw & ge;                        // A: a new heatwave starts
+            const uint32_t Cm = inhw & sublt;                     // C: subsequent event of the current heatwave
+            const uint32_t Dm = inhw & ~sublt;                    // D: subsequent events used up
+            const uint32_t Dn = Dm & ge;                          //    ... long enough: new heatwave id
+            const uint32_t lab = A | Cm | Dn;
+            fresh |= A | Dn;
+            inhw = (inhw | A) & ~(Dm & ~ge);
+            uint32_t borrow = Cm;
+            sublt = 0u;
+#pragma unroll
+            for (int q = 0; q < KS; q++) {                        // rem -= 1 where C, rem = max_subs where D
+                const uint32_t t = ~rem[q] & borrow;
+                rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
+                borrow = t;
+                sublt |= rem[q];
+            }
+            if (lab) {
+                const int days = min(e, b_cur) - max(s, a_cur);
+                if (days > 0) account(lab, (uint32_t)days);
+                if (e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; }
+            }
         }
+        flush();
     }
-    while (ys < n_seasons) flush();
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -545,7 +557,8 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         for (int i = 0; i < D; i++) if (h_defs[3 * i + 1] < g) lut[tabs.ge_len + g] |= 1u << i;
     HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
     const uint32_t *ge_tab = L.lut, *brk_tab = L.lut + tabs.ge_len;
-    const size_t scan_smem = (256 * 4 + lut.size()) * sizeof(uint32_t);
+    const size_t scan_smem = (256 * 4 + lut.size() + (size_t)K + 1) * sizeof(uint32_t);
+    if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~45 000 hot words (~4 000 years of daily data)
     const int pw = std::min(P, 8);
     dim3 block(32, pw);
     dim3 grid((unsigned)((C + 31) / 32), (unsigned)((P + pw - 1) / pw));
@@ -568,6 +581,8 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         const int ns = ip < passes[1].size() ? (int)passes[1][ip].size() : 0;
         KernelTimer timer(kScan, st);
 #define HDP_LAUNCH_SCAN(NP, KS)                                                                                          \
+        if (scan_smem > 48 * 1024)                                                                                       \
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
         k_scan<NP, KS><<<grid, block, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, sn, nn, ss, ns, \
                                                        Y, d_is_south, d_out)
 #define HDP_SCAN_KS(NP)                                                    \

@@ -134,7 +134,7 @@ k_thr_generic(const float *__restrict__ temps, int64_t C, int64_t T_b, int64_t l
 //   4. every requested percentile is read from that single ordering: the k-th and (k+1)-th window members
 //      are found by a popcount prefix scan across lanes and an in-word select, and interpolated in double.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kRankedThreads = 512;
+constexpr int kRankedThreads = 1024;
 constexpr int kRankedWarps = kRankedThreads / 32;
 constexpr int kRadixBits = 4, kRadixBins = 1 << kRadixBits, kRadixPasses = 32 / kRadixBits;
 
@@ -146,6 +146,7 @@ struct SelTable {                    // per percentile, identical for every cell
     int mode[HDP_B200_MAX_PERCENTILES];
     double w_lo[HDP_B200_MAX_PERCENTILES];    // 1 - m
     double w_hi[HDP_B200_MAX_PERCENTILES];    // m
+    int8_t b_slot[64];                        // per warp: index of its plane B (rows pooled twice), -1 = none needed
 };
 
 __device__ __forceinline__ uint32_t f32_to_key(float v)
@@ -275,11 +276,13 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
 
     // ---- 3./4. sliding rank bitmaps, one day-of-year range per warp ----
     const int wpl = nwords_pad >> 5;                              // bitmap words per lane
-    uint32_t *A = planes + (size_t)warp * 2 * nwords_pad, *B = A + nwords_pad;
-    for (int i = lane; i < 2 * nwords_pad; i += 32) A[i] = 0u;
+    // layout: [warp] plane A | [warp] members-in-front-of-word (u16) | plane B of the few warps that need one
+    uint32_t *A = planes + (size_t)warp * nwords_pad;
+    uint16_t *pre = (uint16_t *)(planes + (size_t)kRankedWarps * nwords_pad) + (size_t)warp * nwords_pad;
+    const bool range_dup = sel.b_slot[warp] >= 0;
+    uint32_t *B = planes + (size_t)kRankedWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad;
+    for (int i = lane; i < nwords_pad; i += 32) { A[i] = 0u; if (range_dup) B[i] = 0u; }
     const int d_begin = warp * dpw, d_end = min(n_doy, d_begin + dpw);
-    bool range_dup = false;
-    for (int d = d_begin; d < d_end; d++) range_dup |= doy_dup[d] != 0;
     const int n_nan = s_nonfinite[0], n_pinf = s_nonfinite[1], n_ninf = s_nonfinite[2];
     const bool nonfinite = (n_nan | n_pinf | n_ninf) != 0;
     __syncwarp();
@@ -293,7 +296,7 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
                 const uint32_t bit = 1u << (r & 31);
                 if (op & 1) {
                     const uint32_t old = atomicOr(&A[r >> 5], bit);
-                    if (old & bit) atomicOr(&B[r >> 5], bit);
+                    if (range_dup && (old & bit)) atomicOr(&B[r >> 5], bit);
                 } else {
                     if (range_dup && (B[r >> 5] & bit)) atomicAnd(&B[r >> 5], ~bit);
                     else atomicAnd(&A[r >> 5], ~bit);
@@ -303,13 +306,18 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
         }
         const bool dup = doy_dup[d] != 0;
 
-        // members per lane slice, inclusive scan across lanes
+        // members per lane slice (and the running count in front of every word), inclusive scan across lanes
         int s = 0;
-        for (int i = 0; i < wpl; i++) s += __popc(A[lane * wpl + i]);
-        if (dup) for (int i = 0; i < wpl; i++) s += __popc(B[lane * wpl + i]);
+        if (!dup) {
+#pragma unroll 4
+            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]); }
+        } else {
+            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]) + __popc(B[lane * wpl + i]); }
+        }
         int incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncwarp();
 
         int w_nan = 0, w_pinf = 0, w_ninf = 0;
         if (nonfinite) {                                          // rare: count the window's non-finite members by rank range
@@ -331,16 +339,16 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
             }
             const int owner = lo;
             int rem = target - (__shfl_sync(0xffffffffu, incl, owner) - __shfl_sync(0xffffffffu, s, owner));
-            int w = owner * wpl;
-            uint32_t a = 0u, b = 0u;
-            for (int i = 0; i < wpl; i++, w++) {
-                a = A[w];
-                b = dup ? B[w] : 0u;
-                const int cw = __popc(a) + __popc(b);
-                if (rem < cw) break;
-                rem -= cw;
+            // last word of the owner's slice whose running count is <= rem (binary search over <= 16 words)
+            const uint16_t *pw = pre + owner * wpl;
+            int wl = 0, wh = wpl - 1;
+            while (wl < wh) {
+                const int mid = (wl + wh + 1) >> 1;
+                if ((int)pw[mid] <= rem) wl = mid; else wh = mid - 1;
             }
-            w = min(w, owner * wpl + wpl - 1);
+            const int w = owner * wpl + wl;
+            rem -= pw[wl];
+            const uint32_t a = A[w], b = dup ? B[w] : 0u;
             const int bitpos = dup ? select_in_word<true>(a, b, rem) : select_in_word<false>(a, 0u, rem);
             const int r = min(w * 32 + bitpos, E - 1);
             const double val = (double)key_to_f32(keyA[r]);
@@ -402,7 +410,6 @@ static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, cons
     if (pl.smem > 227 * 1024 - 256) return;
     const int nwords = (int)((E + 31) / 32);
     pl.nwords_pad = (nwords + 31) / 32 * 32;
-    if ((size_t)kRankedWarps * 2 * pl.nwords_pad * 4 > pl.smem - (((size_t)E + 63) & ~(size_t)63) * 6) return;
     pl.dpw = (n_doy + kRankedWarps - 1) / kRankedWarps;
     pl.ept = (int)((E + kRankedThreads - 1) / kRankedThreads) | 1;          // odd: conflict-free strided key reads
     pl.doy_dup.assign(n_doy, 0);
@@ -429,6 +436,14 @@ static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, cons
         prev.swap(cur);
     }
     pl.op_off[n_doy] = (int)pl.ops.size();
+    int n_b = 0;
+    for (int w = 0; w < 64; w++) {
+        pl.sel.b_slot[w] = -1;
+        bool need = false;
+        for (int d = w * pl.dpw; d < std::min(n_doy, (w + 1) * pl.dpw); d++) need |= pl.doy_dup[d] != 0;
+        if (need && w < kRankedWarps) pl.sel.b_slot[w] = (int8_t)n_b++;
+    }
+    if ((size_t)pl.nwords_pad * (kRankedWarps * 6 + n_b * 4) > pl.smem - (((size_t)E + 63) & ~(size_t)63) * 6) return;
     // positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
     for (int p = 0; p < HDP_B200_MAX_PERCENTILES; p++) {
         pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = 0;

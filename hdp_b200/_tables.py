@@ -283,3 +283,34 @@ def clamp_ranges(ranges: np.ndarray, T: int) -> np.ndarray:
 def definition_labels(hw_definitions: Sequence[Sequence[int]]) -> list:
     """Coordinate strings of the ``definition`` dimension (reference hdp/metric.py:347-350)."""
     return [f"{d[0]}-{d[1]}-{d[2]}" for d in hw_definitions]
+
+
+def factor_window_samples(window_samples: np.ndarray) -> WindowTables:
+    """Recover (time_index, win_rows) from the reference's flat ``int[n_doy, W*n_y]`` table.
+
+    ``datetimes_to_windows`` builds every window row as a concatenation of whole ``time_index`` rows, and the centre
+    slot (k = r, sample_index = d) of row d is ``time_index[d]`` itself (reference hdp/threshold.py:41-48).  The number
+    of years per row, n_y, is the largest divisor of the row length for which that structure holds."""
+    win = np.asarray(window_samples, dtype=np.int64)
+    n_doy, b = win.shape
+    for W in range(b if b % 2 else b - 1, 0, -2):            # widest window (fewest years per row) first
+        if b % W:
+            continue
+        n_y = b // W
+        blocks = win.reshape(n_doy, W, n_y)
+        time_index = blocks[:, W // 2, :]
+        lookup = {tuple(row): i for i, row in enumerate(time_index)}
+        rows = np.full((n_doy, W), -1, dtype=np.int64)
+        ok = True
+        for d in range(n_doy):
+            for k in range(W):
+                i = lookup.get(tuple(blocks[d, k]))
+                if i is None:
+                    ok = False
+                    break
+                rows[d, k] = i
+            if not ok:
+                break
+        if ok and len(lookup) == n_doy:
+            return WindowTables(time_index=time_index.copy(), win_rows=rows, radius=W // 2)
+    raise ValueError("window_samples is not a table produced by datetimes_to_windows")

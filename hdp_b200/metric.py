@@ -1,0 +1,153 @@
+"""hdp.metric on B200 (reference hdp/metric.py).
+
+Same function names, arguments, output variables, dims ``(percentile, definition, <cells>, time)``, coordinates,
+dtypes (int64) and attributes as the reference.  The per-cell / per-percentile / per-definition Python -> Numba calls
+(`compute_heatwave_metrics`, metric.py:304-341, swept at :357-369) are replaced by ONE call into libhdp_b200.so that
+covers the whole sweep; the per-day heatwave id array is never built.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _core, _layout, _tables, xr
+from .utils import add_history, get_version, time_axis_of
+
+METRIC_ATTRS = {          # metric.py:473-492
+    "HWF": {"units": "heatwave days", "long_name": "Heatwave Frequency",
+            "description": "Number of days that fall within heatwave during a heatwave season"},
+    "HWD": {"units": "heatwave days", "long_name": "Heatwave Duration",
+            "description": "Length of longest heatwave during a heatwave season"},
+    "HWN": {"units": "heatwave events", "long_name": "Heatwave Number",
+            "description": "Number of distinct heatwaves during a heatwave season"},
+    "HWA": {"units": "heatwave events", "long_name": "Heatwave Average",
+            "description": "Average length of heatwaves during a heatwave season"},
+}
+
+
+def build_doy_map(times) -> np.ndarray:
+    """metric.py:265-277"""
+    axis = times if isinstance(times, _tables.TimeAxis) else _tables.TimeAxis.from_datetimes(list(times))
+    return _tables.doy_map(axis.dayofyr)
+
+
+def get_range_indices(times, start: tuple, end: tuple) -> np.ndarray:
+    """metric.py:175-209"""
+    axis = times if isinstance(times, _tables.TimeAxis) else _tables.TimeAxis.from_datetimes(list(times))
+    return _tables.range_indices(axis, start, end)
+
+
+def compute_hemisphere_ranges(measure):
+    """metric.py:212-262: ``int[year, end_points, lat, lon]`` season table, South for lat < 0."""
+    axis = time_axis_of(measure)
+    st = _tables.hemisphere_ranges(axis)
+    lat, lon = np.asarray(xr.coord_values(measure, "lat")), np.asarray(xr.coord_values(measure, "lon"))
+    ranges = np.where((lat < 0)[None, None, :, None], st.south[:, :, None, None], st.north[:, :, None, None])
+    ranges = np.broadcast_to(ranges, (st.n_years, 2, lat.size, lon.size)).copy()
+    return xr.DataArray(ranges, dims=["year", "end_points", "lat", "lon"],
+                        coords={"year": st.years, "end_points": ["start", "finish"], "lat": lat, "lon": lon})
+
+
+def compute_heatwave_metrics(measure, threshold, doy_map, min_duration, max_break, max_subs, season_ranges) -> np.ndarray:
+    """Array-level seam of the reference kernel (metric.py:304-341) on the GPU, one cell, one definition:
+    float32[t], float64[doy], int[t], 3 ints, int[y, 2] -> int64[4, y] = [HWF, HWN, HWD, HWA]."""
+    x = np.ascontiguousarray(measure, dtype=np.float32).reshape(-1, 1)
+    thr = np.ascontiguousarray(threshold, dtype=np.float64).reshape(1, -1, 1)
+    out = _core.metrics_host(x, thr, doy_map, [[min_duration, max_break, max_subs]], season_ranges, season_ranges)
+    return out[:, 0, 0, :, 0].astype(np.int64)
+
+
+def _year_times(years: np.ndarray, calendar: str):
+    if xr.HAVE_XARRAY:                 # pragma: no cover - cftime Jan-1 stamps, metric.py:463-465
+        import cftime
+        import xarray
+        start_ts = cftime.datetime(int(years[0]), 1, 1, calendar=calendar)
+        end_ts = cftime.datetime(int(years[-1]), 1, 1, calendar=calendar)
+        return xarray.date_range(start_ts, end_ts, periods=years.size, use_cftime=True)
+    n = years.size
+    return _tables.TimeAxis(np.asarray(years, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), calendar)
+
+
+def compute_individual_metrics(measure, threshold, hw_definitions: list, include_threshold: bool = True, check_variables: bool = True):
+    """metric.py:372-506."""
+    time_axis = time_axis_of(measure)
+    if check_variables:                                             # :393-398
+        assert "hdp_type" in threshold.attrs
+        assert threshold.attrs["hdp_type"] == "threshold"
+        assert threshold.attrs["baseline_variable"] == measure.attrs["baseline_variable"]
+        assert threshold.attrs["baseline_calendar"] == time_axis.calendar
+
+    combined_history = ""                                           # :400-408
+    if "history" in measure.attrs:
+        for entry in measure.attrs["history"].split("\n"):
+            if entry != '':
+                combined_history += (f"(Measure) {entry}\n")
+    if "history" in threshold.attrs:
+        for entry in threshold.attrs["history"].split("\n"):
+            if entry != '':
+                combined_history += (f"(Threshold) {entry}\n")
+
+    st = _tables.hemisphere_ranges(time_axis)                       # compute_hemisphere_ranges, :410
+    doy_map = _tables.doy_map(time_axis.dayofyr)                    # build_doy_map, :413
+    x, cell_dims, cell_shape = _layout.to_time_cells(xr.values_of(measure), tuple(measure.dims))
+    south = _tables.is_south(_layout.cell_latitudes(xr.coord_values(measure, "lat"), cell_dims, cell_shape))
+
+    # thresholds [<cells in the measure's order>, doy, percentile] -> [C, n_doy, P]; exact coordinate join like apply_ufunc
+    thr_dims = tuple(threshold.dims)
+    want = [*cell_dims, "doy", "percentile"]
+    if sorted(thr_dims) != sorted(want):
+        raise ValueError(f"threshold dims {thr_dims} do not match measure dims {tuple(measure.dims)}")
+    for d in cell_dims:
+        if not np.array_equal(np.asarray(xr.coord_values(threshold, d)), np.asarray(xr.coord_values(measure, d))):
+            raise ValueError(f"cannot align measure and threshold exactly along '{d}'")
+    thr_vals = np.transpose(xr.values_of(threshold), [thr_dims.index(d) for d in want]).astype(np.float64, copy=False)
+    n_doy, P = thr_vals.shape[-2], thr_vals.shape[-1]
+    thr_cdp = np.ascontiguousarray(thr_vals).reshape(-1, n_doy, P)
+
+    defs = np.asarray(hw_definitions, dtype=np.int64).reshape(-1, 3)
+    out = _core.metrics_host(x, thr_cdp, doy_map, defs, st.north, st.south, south)     # uint16 [4, P, D, Y, C]
+    D, Y = defs.shape[0], st.n_years
+
+    coords = dict(xr.non_time_coords(measure))
+    coords["definition"] = [f"{hw_def[0]}-{hw_def[1]}-{hw_def[2]}" for hw_def in hw_definitions]   # :432
+    coords["percentile"] = np.asarray(xr.coord_values(threshold, "percentile"))
+    coords["time"] = _year_times(st.years, time_axis.calendar)
+    dims = ["percentile", "definition", *cell_dims, "time"]
+    data_vars = {}
+    for i, name in enumerate(_core.METRIC_NAMES):                   # HWF=0, HWN=1, HWD=2, HWA=3, :454-461
+        plane = out[i].transpose(0, 1, 3, 2).reshape(P, D, *cell_shape, Y)              # view: no host transposition
+        data_vars[name] = xr.DataArray(plane.astype(np.int64), dims=dims, coords=coords)
+    ds = xr.Dataset(data_vars)
+    ds.attrs.update({
+        "description": f"Heatwave metric dataset generated by Heatwave Diagnostics Package (HDP v{get_version()})",
+        "hdp_version": get_version(),
+        "hdp_type": "metric"
+    })
+    for name, attrs in METRIC_ATTRS.items():
+        ds[name].attrs.update(attrs)
+    xr.set_coord_attrs(ds, "percentile", {"range": "(0, 1)"})
+    xr.set_coord_attrs(ds, "definition", {
+        "first_number": "Minimum number of consecutively hot days",
+        "second_number": "Maximum number of break days after first wave",
+        "third_number": "Minimum number of consecutively hot days after the break"
+    })
+    for variable in ds:
+        ds[variable].attrs["history"] = combined_history
+        add_history(ds[variable], f"Heatwave metrics generated by HDP v{get_version()}")
+    return ds
+
+
+def compute_group_metrics(measures, thresholds, hw_definitions: list, include_threshold: bool = False, check_variables: bool = True):
+    """metric.py:509-523: every measure against every threshold of the same baseline variable."""
+    metric_sets = []
+    for measure_name in list(measures.keys()):
+        measure = measures[measure_name]
+        for threshold_name in list(thresholds.keys()):
+            threshold = thresholds[threshold_name]
+            if threshold.attrs["baseline_variable"] == measure.attrs["baseline_variable"]:
+                hw_metrics = compute_individual_metrics(measure, threshold, hw_definitions, include_threshold, check_variables)
+                var_renames = {name: f"{measure_name}.{threshold_name}.{name}" for name in list(hw_metrics.keys())}
+                metric_sets.append(hw_metrics.rename(var_renames))
+    aggr_ds = xr.merge(metric_sets)
+    aggr_ds.attrs["variable_naming_desc"] = "(heat measure).(threshold used).(heatwave metric)"
+    aggr_ds.attrs["variable_naming_delimeter"] = "."
+    return aggr_ds

@@ -46,7 +46,7 @@ def seasonal_series(rng, axis: TimeAxis, n_cells: int, trend: float = 0.0, noise
 
 
 def main():
-    thr_mod, met_mod, _ = ref_numba.load()
+    thr_mod, met_mod, mea_mod = ref_numba.load()
     import numba
     meta = dict(numba=numba.__version__, numpy=np.__version__)
     print("reference loaded; numba", numba.__version__)
@@ -178,6 +178,17 @@ def main():
         print(name, "hot fraction p0:", float(np.mean(x > thr[np.arange(ncell)[None, :], doy_map[:, None], 0])))
     np.savez_compressed(os.path.join(HERE, "metrics.npz"), **met)
     print("metrics.npz", len(met))
+    # ---------------------------------------------------------------- heat index (measure.py:61-94)
+    t = rng.uniform(40, 125, 20000).astype(np.float32)
+    rh = rng.uniform(0, 100, 20000).astype(np.float32)
+    t[:2000] = rng.uniform(79, 113, 2000).astype(np.float32)      # the two adjustment regimes
+    rh[:1000] = rng.uniform(0, 14, 1000).astype(np.float32)
+    rh[1000:2000] = rng.uniform(84, 100, 1000).astype(np.float32)
+    t[1000:2000] = rng.uniform(79, 88, 1000).astype(np.float32)
+    t[2000:2010] = [80, 87, 112, 95, 80.00001, 79.99999, 68, 0, -40, 150]
+    rh[2000:2010] = [13, 85, 12.9, 0, 85.1, 50, 100, 50, 50, 100]
+    np.savez_compressed(os.path.join(HERE, "measure.npz"), t=t, rh=rh, hi=mea_mod.heat_index(t, rh))
+    print("measure.npz")
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write("golden fixtures generated by tests/golden/make_golden.py from the unmodified reference\n")
         f.write("reference: AgentOxygen/HDP v1.0.2 at /root/reference\n")

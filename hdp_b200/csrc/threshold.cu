@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kRankedThreads, 1)
 k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
              const int *__restrict__ time_index, int E, int n_y, int n_doy, int n,
              const int *__restrict__ op_off, const int *__restrict__ ops, const uint8_t *__restrict__ doy_dup,
-             int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out)
+             int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out,
+             const int *__restrict__ cell_count, const int *__restrict__ cell_list)
 {
     constexpr int NT = kRankedThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,8 +213,12 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
     __shared__ int s_warp_tot[kRankedWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t c = blockIdx.x;
+    // cells: blockIdx.x itself, or (as the hand-over target of k_thr_cell) the entries of a device-side list
+    const int n_cells = cell_list ? *cell_count : (int)gridDim.x;
+    for (int ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
+    const int64_t c = cell_list ? cell_list[ci] : ci;
 
+    __syncthreads();
     if (tid < 3) s_nonfinite[tid] = 0;
     __syncthreads();
 
@@ -378,6 +383,333 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
             }
         }
     }
+}   // cells
+}
+
+// ----------------------------------------------------------------------------------------------------
+// k_thr_cell: the current fast path.  One CTA per cell, same plan as k_thr_ranked (order the cell's samples once,
+// slide a rank bitmap over the days of year) with a cheaper ordering stage:
+//
+//   1. gather the E = n_doy * n_y elements into shared memory (batched independent loads), find the finite
+//      min / max and count NaN / +inf / -inf;
+//   2. quantise every sample to a MONOTONE 16-bit bucket  b = 1 + trunc((v - vmin) * 65532 / (vmax - vmin))
+//      (float subtraction, multiplication and truncation are all monotone, so bucket order never contradicts
+//      value order; -inf -> 0, +inf -> 65534, NaN -> 65535) and pack (bucket << 16 | element) into ONE word;
+//   3. stable LSD radix sort of the packed words on the bucket: 4 passes of 4 bits instead of 8 passes over
+//      (key, element) pairs.  Digit counters are private per thread, two digits per 32-bit word, in an
+//      XOR-swizzled layout so that both the per-thread updates and the 64-byte-per-thread scan are free of
+//      bank conflicts;
+//   4. samples that share a bucket are adjacent now; each run is put in true order by its first owner thread
+//      (insertion sort on the exact float keys; runs are 1-3 long for real temperature data).  A cell whose
+//      samples pile into one bucket (an outlier stretching the range) is handed to k_thr_ranked through a
+//      device-side list instead;
+//   5./6. rank bitmaps and percentile selection exactly as in k_thr_ranked.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kCellThreads = 1024;
+constexpr int kCellWarps = kCellThreads / 32;
+constexpr int kMaxTieRun = 48;
+
+__global__ void __launch_bounds__(kCellThreads, 1)
+k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
+           const int *__restrict__ time_index, int E, int n_y, int n_doy, int n,
+           const int *__restrict__ op_off, const int *__restrict__ ops, const uint8_t *__restrict__ doy_dup,
+           int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out,
+           int *__restrict__ fallback_count, int *__restrict__ fallback_cells)
+{
+    constexpr int NT = kCellThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Epad = (E + 63) & ~63;
+    float *x = (float *)smem_raw;                                 // samples by element
+    uint32_t *PA = (uint32_t *)(x + Epad);                        // packed (bucket << 16 | element), sorted at the end
+    uint32_t *PB = PA + Epad;                                     // second sort buffer; sorted VALUES afterwards
+    uint32_t *Wc = PB + Epad;                                     // [8][NT] digit counters (two digits per word), swizzled
+    float *V = (float *)PB;
+    uint16_t *rank_of = (uint16_t *)Wc;                           // after the sort
+    uint32_t *planes = (uint32_t *)x;                             // after the sort: bitmaps over x + PA
+    __shared__ int s_nonfinite[3];                                // NaN, +inf, -inf elements of this cell
+    __shared__ float s_min[kCellWarps], s_max[kCellWarps];
+    __shared__ uint32_t s_tot[kCellWarps];
+    __shared__ int s_fallback;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t c = blockIdx.x;
+
+    if (tid < 3) s_nonfinite[tid] = 0;
+    if (tid == 0) s_fallback = 0;
+    __syncthreads();
+
+    // ---- 1. gather (loads issued four at a time, independent of each other) ----
+    const float pinf = __int_as_float(0x7f800000);
+    float vmin = pinf, vmax = -pinf;
+    int c_nan = 0, c_pinf = 0, c_ninf = 0;
+    for (int e4 = tid; e4 < E; e4 += 4 * NT) {
+        int64_t t[4];
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e4 + i * NT;
+            t[i] = e < E ? time_index[e] : 0;
+            if (t[i] < 0) t[i] += T_b;                            // -1 pads read the LAST sample (threshold.py:35,77)
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = temps[t[i] * ld_t + c];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e4 + i * NT;
+            if (e < E) {
+                x[e] = v[i];
+                if (v[i] != v[i]) c_nan++;
+                else if (v[i] == pinf) c_pinf++;
+                else if (v[i] == -pinf) c_ninf++;
+                else { vmin = fminf(vmin, v[i]); vmax = fmaxf(vmax, v[i]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    c_nan = __reduce_add_sync(0xffffffffu, c_nan);
+    c_pinf = __reduce_add_sync(0xffffffffu, c_pinf);
+    c_ninf = __reduce_add_sync(0xffffffffu, c_ninf);
+    if (lane == 0) {
+        s_min[warp] = vmin; s_max[warp] = vmax;
+        if (c_nan) atomicAdd(&s_nonfinite[0], c_nan);
+        if (c_pinf) atomicAdd(&s_nonfinite[1], c_pinf);
+        if (c_ninf) atomicAdd(&s_nonfinite[2], c_ninf);
+    }
+    __syncthreads();
+    vmin = s_min[lane]; vmax = s_max[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+
+    // ---- 2. monotone 16-bit buckets, packed with the element index ----
+    const float range = vmax - vmin;
+    const float scale = (range > 0.0f && range < pinf) ? 65532.0f / range : 0.0f;
+    for (int e = tid; e < E; e += NT) {
+        const float v = x[e];
+        uint32_t b;
+        if (v != v) b = 65535u;
+        else if (v == pinf) b = 65534u;
+        else if (v == -pinf) b = 0u;
+        else b = 1u + (uint32_t)min(65532, max(0, __float2int_rz((v - vmin) * scale)));
+        PA[e] = (b << 16) | (uint32_t)e;
+    }
+    __syncthreads();
+
+    // ---- 3. stable LSD radix sort on the bucket: 4 passes x 4 bits ----
+    {
+        uint32_t *src = PA, *dst = PB;
+        const int e0 = min(tid * ept, E), e1 = min(e0 + ept, E);
+        // word of digit pair k of this thread: k * NT + tsw (16-byte pieces XOR-swizzled inside groups of 8)
+        const int tsw = ((((tid >> 2) ^ (warp & 7)) << 2) | (tid & 3));
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 16 + 4 * pass;
+#pragma unroll
+            for (int k = 0; k < 8; k++) Wc[k * NT + tsw] = 0u;
+            // (no barrier needed: every thread only touches its own 8 words until the scan)
+            for (int e = e0; e < e1; e++) {
+                const uint32_t d = (src[e] >> shift) & 15u;
+                Wc[(d >> 1) * NT + tsw] += 1u << ((d & 1u) << 4);
+            }
+            __syncthreads();
+            // exclusive scan in (digit, thread) order.  Thread u < 512 owns 16 consecutive words of one digit pair
+            // (both halves): chunk u -> pair k = u >> 6, threads 16 * (u & 63) ... + 15.
+            uint32_t ex[16], run = 0u, incl = 0u;
+            uint4 *W4 = reinterpret_cast<uint4 *>(Wc);
+            const int sw = (tid >> 1) & 7;
+            if (tid < 512) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 q = W4[(4 * tid + j) ^ sw];
+                    ex[4 * j + 0] = q.x; ex[4 * j + 1] = q.y; ex[4 * j + 2] = q.z; ex[4 * j + 3] = q.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) { const uint32_t w = ex[j]; ex[j] = run; run += w; }   // packed lo | hi << 16
+                incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (lane == 31) s_tot[warp] = incl;
+            }
+            __syncthreads();
+            if (tid < 512) {
+                const int g0 = warp & ~1;                         // first warp of this digit pair
+                const uint32_t t = lane < 16 ? s_tot[lane] : 0u;
+                const uint32_t before = __reduce_add_sync(0xffffffffu, lane < g0 ? t : 0u);
+                const uint32_t t0 = __shfl_sync(0xffffffffu, t, g0), t1 = __shfl_sync(0xffffffffu, t, g0 + 1);
+                const uint32_t before_all = (before & 0xffffu) + (before >> 16);
+                const uint32_t grp = warp == g0 ? 0u : t0;        // warps of this pair in front of this one
+                const uint32_t exw = incl - run;                  // threads of this warp in front of this one
+                const uint32_t base_lo = before_all + (grp & 0xffffu) + (exw & 0xffffu);
+                const uint32_t base_hi = before_all + ((t0 + t1) & 0xffffu) + (grp >> 16) + (exw >> 16);
+#pragma unroll
+                for (int j = 0; j < 16; j++) ex[j] = (base_lo + (ex[j] & 0xffffu)) | ((base_hi + (ex[j] >> 16)) << 16);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    W4[(4 * tid + j) ^ sw] = make_uint4(ex[4 * j + 0], ex[4 * j + 1], ex[4 * j + 2], ex[4 * j + 3]);
+            }
+            __syncthreads();
+            for (int e = e0; e < e1; e++) {
+                const uint32_t w = src[e];
+                const uint32_t d = (w >> shift) & 15u, sh = (d & 1u) << 4;
+                uint32_t *cw = &Wc[(d >> 1) * NT + tsw];
+                const uint32_t cv = *cw;
+                *cw = cv + (1u << sh);
+                dst[(cv >> sh) & 0xffffu] = w;
+            }
+            __syncthreads();
+            uint32_t *tp = src; src = dst; dst = tp;
+        }
+        // four passes: the sorted words are back in PA
+
+        // ---- 4. exact order inside runs of equal bucket ----
+        for (int i = e0; i < e1; i++) {
+            const uint32_t b = PA[i] >> 16;
+            if (i > 0 && (PA[i - 1] >> 16) == b) continue;        // not the start of a run
+            if (b == 0u || b >= 65534u) continue;                 // -inf / +inf / NaN: identical keys
+            int j = i + 1;
+            while (j < E && (PA[j] >> 16) == b) j++;
+            if (j - i == 1) continue;
+            if (j - i > kMaxTieRun) {                             // long run: fine if already ordered (ties), else hand over
+                bool ordered = true;
+                uint32_t kp = f32_to_key(x[PA[i] & 0xffffu]);
+                for (int a = i + 1; a < j && ordered; a++) {
+                    const uint32_t ka = f32_to_key(x[PA[a] & 0xffffu]);
+                    ordered = ka >= kp;
+                    kp = ka;
+                }
+                if (!ordered) s_fallback = 1;
+                continue;
+            }
+            for (int a = i + 1; a < j; a++) {
+                const uint32_t wa = PA[a];
+                const uint32_t ka = f32_to_key(x[wa & 0xffffu]);
+                int bpos = a;
+                while (bpos > i) {
+                    const uint32_t wb = PA[bpos - 1];
+                    if (f32_to_key(x[wb & 0xffffu]) <= ka) break;
+                    PA[bpos] = wb;
+                    bpos--;
+                }
+                PA[bpos] = wa;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_fallback) {                                             // block-uniform
+        if (tid == 0) fallback_cells[atomicAdd(fallback_count, 1)] = (int)c;
+        return;
+    }
+    for (int r = tid; r < E; r += NT) {
+        const uint32_t idx = PA[r] & 0xffffu;
+        V[r] = x[idx];
+        rank_of[idx] = (uint16_t)r;
+    }
+    __syncthreads();
+
+    // ---- 5./6. sliding rank bitmaps, one day-of-year range per warp (see k_thr_ranked) ----
+    const int wpl = nwords_pad >> 5;
+    uint32_t *A = planes + (size_t)warp * nwords_pad;
+    uint16_t *pre = (uint16_t *)(planes + (size_t)kCellWarps * nwords_pad) + (size_t)warp * nwords_pad;
+    const bool range_dup = sel.b_slot[warp] >= 0;
+    uint32_t *B = planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad;
+    for (int i = lane; i < nwords_pad; i += 32) { A[i] = 0u; if (range_dup) B[i] = 0u; }
+    const int d_begin = warp * dpw, d_end = min(n_doy, d_begin + dpw);
+    const int n_nan = s_nonfinite[0], n_pinf = s_nonfinite[1], n_ninf = s_nonfinite[2];
+    const bool nonfinite = (n_nan | n_pinf | n_ninf) != 0;
+    __syncwarp();
+
+    for (int d = d_begin; d < d_end; d++) {
+        for (int o = op_off[d]; o < op_off[d + 1]; o++) {
+            const int op = ops[o], row = op >> 1;
+            for (int j = lane; j < n_y; j += 32) {
+                const int r = rank_of[row * n_y + j];
+                const uint32_t bit = 1u << (r & 31);
+                if (op & 1) {
+                    const uint32_t old = atomicOr(&A[r >> 5], bit);
+                    if (range_dup && (old & bit)) atomicOr(&B[r >> 5], bit);
+                } else {
+                    if (range_dup && (B[r >> 5] & bit)) atomicAnd(&B[r >> 5], ~bit);
+                    else atomicAnd(&A[r >> 5], ~bit);
+                }
+            }
+            __syncwarp();
+        }
+        const bool dup = doy_dup[d] != 0;
+
+        int s = 0;
+        if (!dup) {
+#pragma unroll 4
+            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]); }
+        } else {
+            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]) + __popc(B[lane * wpl + i]); }
+        }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncwarp();
+
+        int w_nan = 0, w_pinf = 0, w_ninf = 0;
+        if (nonfinite) {
+            w_ninf = range_count(A, B, dup, wpl, lane, 0, n_ninf);
+            w_pinf = range_count(A, B, dup, wpl, lane, E - n_nan - n_pinf, E - n_nan);
+            w_nan = range_count(A, B, dup, wpl, lane, E - n_nan, E);
+        }
+
+        for (int p0 = 0; p0 < P; p0 += 16) {
+            const int p = min(p0 + (lane >> 1), P - 1);
+            const int target = (lane & 1) ? sel.pos_hi[p] : sel.pos_lo[p];
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi) >> 1;
+                const int v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > target) hi = mid; else lo = mid + 1;
+            }
+            const int owner = lo;
+            int rem = target - (__shfl_sync(0xffffffffu, incl, owner) - __shfl_sync(0xffffffffu, s, owner));
+            const uint16_t *pw = pre + owner * wpl;
+            int wl = 0, wh = wpl - 1;
+            while (wl < wh) {
+                const int mid = (wl + wh + 1) >> 1;
+                if ((int)pw[mid] <= rem) wl = mid; else wh = mid - 1;
+            }
+            const int w = owner * wpl + wl;
+            rem -= pw[wl];
+            const uint32_t a = A[w], b = dup ? B[w] : 0u;
+            const int bitpos = dup ? select_in_word<true>(a, b, rem) : select_in_word<false>(a, 0u, rem);
+            const int r = min(w * 32 + bitpos, E - 1);
+            const float valf = V[r];
+            const double lower = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2);
+            const double upper = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2 + 1);
+            if (lane < 16 && p0 + lane < P) {
+                const int pp = p0 + lane, mode = sel.mode[pp];
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                double v;
+                if (mode == kSelInterp) {                         // arraymath.py:1697-1701
+                    v = __dadd_rn(__dmul_rn(lower, sel.w_lo[pp]), __dmul_rn(upper, sel.w_hi[pp]));
+                } else if (mode == kSelMax) {                     // arraymath.py:1669-1675
+                    v = upper;
+                    if ((w_pinf | w_ninf) && isinf(v)) v = nan;
+                } else {                                          // arraymath.py:1678-1695
+                    v = lower;
+                    if (w_pinf | w_ninf) {
+                        const int n_fin = n - (w_pinf + w_ninf);
+                        if (n_fin == 0) v = nan;
+                        if (w_pinf == 1 && n == 2) v = nan;
+                        if (w_ninf > 1) v = nan;
+                        if (n_fin == 1 && w_pinf > 1 && w_ninf != 1) v = nan;
+                    }
+                }
+                if (w_nan > 0) v = nan;                           // _can_collect_percentiles, arraymath.py:1714
+                out[(c * n_doy + d) * (int64_t)P + pp] = v;
+            }
+        }
+    }
 }
 
 static bool bad_dims(int64_t C, int64_t T_b, int n_doy, int n_y, int W, int P)
@@ -392,6 +724,7 @@ struct RankedPlan {
     std::vector<uint8_t> doy_dup;       // window pools some row twice
     int dpw = 0, ept = 0, nwords_pad = 0;
     size_t smem = 0;
+    size_t smem_cell = 0;               // k_thr_cell (0 = its bitmaps do not fit: use k_thr_ranked for every cell)
     SelTable sel;
 };
 
@@ -444,6 +777,13 @@ static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, cons
         if (need && w < kRankedWarps) pl.sel.b_slot[w] = (int8_t)n_b++;
     }
     if ((size_t)pl.nwords_pad * (kRankedWarps * 6 + n_b * 4) > pl.smem - (((size_t)E + 63) & ~(size_t)63) * 6) return;
+    {
+        const size_t Epad = ((size_t)E + 63) & ~(size_t)63;
+        const size_t need = Epad * 12 + (size_t)8 * kCellThreads * 4;
+        const bool planes_fit = (size_t)pl.nwords_pad * (kCellWarps * 6 + n_b * 4) <= Epad * 8;
+        const bool ranks_fit = Epad * 2 <= (size_t)8 * kCellThreads * 4;
+        pl.smem_cell = (need <= 227 * 1024 - 1024 && planes_fit && ranks_fit) ? need : 0;
+    }
     // positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
     for (int p = 0; p < HDP_B200_MAX_PERCENTILES; p++) {
         pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = 0;
@@ -473,6 +813,7 @@ struct ThrLayout {
     size_t total = 0;
     float *xn = nullptr;
     int *time_index = nullptr, *win_rows = nullptr, *op_off = nullptr, *ops = nullptr;
+    int *fallback = nullptr;            // [1 + C]: count, then the cells k_thr_cell hands over to k_thr_ranked
     uint8_t *doy_dup = nullptr;
 };
 
@@ -486,11 +827,13 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.op_off = cv.take<int>((size_t)n_doy + 1);
     L.ops = cv.take<int>((size_t)2 * W * (n_doy + kRankedWarps));           // <= 2W changes per day, W per range start
     L.doy_dup = cv.take<uint8_t>((size_t)n_doy);
+    L.fallback = cv.take<int>((size_t)C + 1);
     L.total = cv.off;
     return L;
 }
 
-static int g_force_generic = 0;
+static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_cell
+static int g_force_ranked = 0;
 
 }  // namespace hdp
 
@@ -498,7 +841,7 @@ using namespace hdp;
 
 extern "C" {
 
-void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on; }
+void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                                            int n_doy, int n_y, int W, int P)
@@ -550,10 +893,29 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
         HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_dup, plan.doy_dup.data(), plan.doy_dup.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        if (plan.smem_cell && !g_force_ranked) {
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_cell));
+            HDP_CUDA_TRY(cudaMemsetAsync(L.fallback, 0, sizeof(int), st));
+            {
+                KernelTimer timer(kThrSort, st);
+                k_thr_cell<<<(unsigned)C, kCellThreads, plan.smem_cell, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
+                                                                            L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
+                                                                            plan.sel, P, d_out, L.fallback, L.fallback + 1);
+                HDP_LAUNCH_CHECK();
+            }
+            // cells whose samples pile into one bucket (rare): a few persistent CTAs walk the device-side list
+            KernelTimer timer(kThrSelect, st);
+            const unsigned grid = (unsigned)std::min<int64_t>(C, 148);
+            k_thr_ranked<<<grid, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
+                                                                 L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
+                                                                 plan.sel, P, d_out, L.fallback, L.fallback + 1);
+            HDP_LAUNCH_CHECK();
+            return HDP_B200_OK;
+        }
         KernelTimer timer(kThrSort, st);
         k_thr_ranked<<<(unsigned)C, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
                                                                     L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
-                                                                    plan.sel, P, d_out);
+                                                                    plan.sel, P, d_out, nullptr, nullptr);
         HDP_LAUNCH_CHECK();
         return HDP_B200_OK;
     }

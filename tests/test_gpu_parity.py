@@ -32,11 +32,12 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
-@pytest.fixture(params=["ranked", "generic"])
+@pytest.fixture(params=["cell", "ranked", "generic"])
 def thr_path(request, core):
-    """Both threshold kernels: the ranked fast path and the generic gather+sort fallback."""
+    """All three threshold kernels: the fast path (k_thr_cell, which hands badly conditioned cells to k_thr_ranked),
+    k_thr_ranked for every cell, and the generic gather+sort fallback."""
     from hdp_b200 import _lib
-    _lib.lib().hdp_b200_thresholds_force_generic(1 if request.param == "generic" else 0)
+    _lib.lib().hdp_b200_thresholds_force_generic({"cell": 0, "generic": 1, "ranked": 2}[request.param])
     yield request.param
     _lib.lib().hdp_b200_thresholds_force_generic(0)
 
@@ -74,6 +75,10 @@ def test_thresholds_random_vs_oracle(core, thr_path):
     x[rng.integers(0, len(ax), 20), rng.integers(0, C, 20)] = -np.inf
     x[:, 5] = np.round(x[:, 5])                               # heavy ties
     x[:, 6] = 1.5                                             # constant series
+    x[100, 7] = 1e30                                          # one outlier squeezes every other sample into one bucket
+    x[200, 8], x[300, 8] = -3e38, 3e38                        # finite range overflows float
+    x[:, 9] = np.where(rng.random(len(ax)) < 0.5, 1e20, x[:, 9])   # half fill values
+    x[:, 10] = np.float32(20.0) + np.arange(len(ax), dtype=np.float32) * np.float32(2e-6)   # many distinct values per bucket
     q = np.array([0.0, 0.1, 0.5, 0.9, 0.95, 0.999, 1.0])
     want = oracle.thresholds_batch(x, wt.window_samples(), q)
     got = core.thresholds_array(dev(x), wt, q).cpu().numpy()

@@ -405,6 +405,16 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
 //      device-side list instead;
 //   5./6. rank bitmaps and percentile selection exactly as in k_thr_ranked.
 // ----------------------------------------------------------------------------------------------------
+// 32-bit shared-state-space accesses: no generic -> shared conversion in front of every atomic
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_and(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_or(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+
 constexpr int kCellThreads = 1024;
 constexpr int kCellWarps = kCellThreads / 32;
 constexpr int kMaxTieRun = 48;
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(kCellThreads, 1)
 k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
            const int *__restrict__ time_index, int E, int n_y, int n_doy, int n,
            const int *__restrict__ op_off, const int *__restrict__ ops, const uint8_t *__restrict__ doy_dup,
-           int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out,
+           int n_ops, int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out,
            int *__restrict__ fallback_count, int *__restrict__ fallback_cells)
 {
     constexpr int NT = kCellThreads;
@@ -567,35 +577,43 @@ k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
         // four passes: the sorted words are back in PA
 
         // ---- 4. exact order inside runs of equal bucket ----
-        for (int i = e0; i < e1; i++) {
-            const uint32_t b = PA[i] >> 16;
-            if (i > 0 && (PA[i - 1] >> 16) == b) continue;        // not the start of a run
-            if (b == 0u || b >= 65534u) continue;                 // -inf / +inf / NaN: identical keys
-            int j = i + 1;
-            while (j < E && (PA[j] >> 16) == b) j++;
-            if (j - i == 1) continue;
-            if (j - i > kMaxTieRun) {                             // long run: fine if already ordered (ties), else hand over
-                bool ordered = true;
-                uint32_t kp = f32_to_key(x[PA[i] & 0xffffu]);
-                for (int a = i + 1; a < j && ordered; a++) {
-                    const uint32_t ka = f32_to_key(x[PA[a] & 0xffffu]);
-                    ordered = ka >= kp;
-                    kp = ka;
+        if (e0 < e1) {
+            uint32_t prev_b = e0 > 0 ? PA[e0 - 1] >> 16 : 0xffffffffu;
+            uint32_t w_cur = PA[e0];
+            for (int i = e0; i < e1; i++) {
+                const uint32_t b = w_cur >> 16;
+                const uint32_t w_next = i + 1 < E ? PA[i + 1] : 0xffffffffu;
+                const bool start = b != prev_b;
+                prev_b = b;
+                w_cur = w_next;
+                if (!start || (w_next >> 16) != b || i + 1 >= E) continue;   // not a run start, or a run of one
+                if (b == 0u || b >= 65534u) continue;             // -inf / +inf / NaN: identical keys
+                int j = i + 2;
+                while (j < E && (PA[j] >> 16) == b) j++;
+                if (j - i > kMaxTieRun) {                         // long run: fine if already ordered (ties), else hand over
+                    bool ordered = true;
+                    uint32_t kp = f32_to_key(x[PA[i] & 0xffffu]);
+                    for (int a = i + 1; a < j && ordered; a++) {
+                        const uint32_t ka = f32_to_key(x[PA[a] & 0xffffu]);
+                        ordered = ka >= kp;
+                        kp = ka;
+                    }
+                    if (!ordered) s_fallback = 1;
+                    continue;
                 }
-                if (!ordered) s_fallback = 1;
-                continue;
-            }
-            for (int a = i + 1; a < j; a++) {
-                const uint32_t wa = PA[a];
-                const uint32_t ka = f32_to_key(x[wa & 0xffffu]);
-                int bpos = a;
-                while (bpos > i) {
-                    const uint32_t wb = PA[bpos - 1];
-                    if (f32_to_key(x[wb & 0xffffu]) <= ka) break;
-                    PA[bpos] = wb;
-                    bpos--;
+                for (int a = i + 1; a < j; a++) {
+                    const uint32_t wa = PA[a];
+                    const uint32_t ka = f32_to_key(x[wa & 0xffffu]);
+                    int bpos = a;
+                    while (bpos > i) {
+                        const uint32_t wb = PA[bpos - 1];
+                        if (f32_to_key(x[wb & 0xffffu]) <= ka) break;
+                        PA[bpos] = wb;
+                        bpos--;
+                    }
+                    PA[bpos] = wa;
                 }
-                PA[bpos] = wa;
+                if (i + 1 < e1) w_cur = PA[i + 1];                // the run was permuted: re-read the next word
             }
         }
     }
@@ -604,49 +622,76 @@ k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
         if (tid == 0) fallback_cells[atomicAdd(fallback_count, 1)] = (int)c;
         return;
     }
+    uint16_t *s_opoff = rank_of + Epad;                           // [n_doy + 1] op offsets, then the ops (u16: row << 1 | enter)
+    uint16_t *s_ops = s_opoff + ((n_doy + 2) & ~1);
     for (int r = tid; r < E; r += NT) {
         const uint32_t idx = PA[r] & 0xffffu;
         V[r] = x[idx];
         rank_of[idx] = (uint16_t)r;
     }
+    for (int i = tid; i <= n_doy; i += NT) s_opoff[i] = (uint16_t)op_off[i];
+    for (int i = tid; i < n_ops; i += NT) s_ops[i] = (uint16_t)ops[i];
     __syncthreads();
 
-    // ---- 5./6. sliding rank bitmaps, one day-of-year range per warp (see k_thr_ranked) ----
+    // ---- 5./6. sliding rank bitmaps, one day-of-year range per warp (algorithm of k_thr_ranked; the tables live
+    //      in shared memory, shared-space addresses are 32-bit, per-lane selection constants are hoisted) ----
     const int wpl = nwords_pad >> 5;
-    uint32_t *A = planes + (size_t)warp * nwords_pad;
-    uint16_t *pre = (uint16_t *)(planes + (size_t)kCellWarps * nwords_pad) + (size_t)warp * nwords_pad;
     const bool range_dup = sel.b_slot[warp] >= 0;
-    uint32_t *B = planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad;
-    for (int i = lane; i < nwords_pad; i += 32) { A[i] = 0u; if (range_dup) B[i] = 0u; }
+    const uint32_t sA = smem_u32(planes + (size_t)warp * nwords_pad);
+    const uint32_t sPre = smem_u32((uint16_t *)(planes + (size_t)kCellWarps * nwords_pad) + (size_t)warp * nwords_pad);
+    const uint32_t sB = smem_u32(planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad);
+    const uint32_t sRank = smem_u32(rank_of);
+    for (int i = lane; i < nwords_pad; i += 32) { sts_u32(sA + 4 * i, 0u); if (range_dup) sts_u32(sB + 4 * i, 0u); }
     const int d_begin = warp * dpw, d_end = min(n_doy, d_begin + dpw);
     const int n_nan = s_nonfinite[0], n_pinf = s_nonfinite[1], n_ninf = s_nonfinite[2];
     const bool nonfinite = (n_nan | n_pinf | n_ninf) != 0;
+    const uint32_t *A = planes + (size_t)warp * nwords_pad;       // generic views for the rare non-finite bookkeeping
+    const uint32_t *B = planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad;
+
+    // lane 2i -> lower pick of percentile i, lane 2i+1 -> upper pick; lanes 0..15 finish percentile `lane`
+    const int n_rounds = (P + 15) >> 4;
+    int tgt[2], md[2];
+    double w_lo[2], w_hi[2];
+#pragma unroll
+    for (int rnd = 0; rnd < 2; rnd++) {
+        const int p = min(rnd * 16 + (lane >> 1), P - 1), pp = min(rnd * 16 + (lane & 15), P - 1);
+        tgt[rnd] = (lane & 1) ? sel.pos_hi[p] : sel.pos_lo[p];
+        md[rnd] = sel.mode[pp]; w_lo[rnd] = sel.w_lo[pp]; w_hi[rnd] = sel.w_hi[pp];
+    }
     __syncwarp();
 
+    int o1 = d_begin < d_end ? s_opoff[d_begin] : 0;
     for (int d = d_begin; d < d_end; d++) {
-        for (int o = op_off[d]; o < op_off[d + 1]; o++) {
-            const int op = ops[o], row = op >> 1;
+        // rows leaving / entering the window (multiset difference to the previous day; full build on the first)
+        const int o0 = o1;
+        o1 = s_opoff[d + 1];
+        for (int o = o0; o < o1; o++) {
+            const uint32_t op = s_ops[o], row = op >> 1;
             for (int j = lane; j < n_y; j += 32) {
-                const int r = rank_of[row * n_y + j];
-                const uint32_t bit = 1u << (r & 31);
-                if (op & 1) {
-                    const uint32_t old = atomicOr(&A[r >> 5], bit);
-                    if (range_dup && (old & bit)) atomicOr(&B[r >> 5], bit);
+                const uint32_t r = lds_u16(sRank + 2u * (row * n_y + j));
+                const uint32_t bit = 1u << (r & 31u), wo = (r >> 5) << 2;
+                if (!range_dup) {
+                    if (op & 1u) reds_or(sA + wo, bit); else reds_and(sA + wo, ~bit);
+                } else if (op & 1u) {
+                    if (atoms_or(sA + wo, bit) & bit) reds_or(sB + wo, bit);
                 } else {
-                    if (range_dup && (B[r >> 5] & bit)) atomicAnd(&B[r >> 5], ~bit);
-                    else atomicAnd(&A[r >> 5], ~bit);
+                    if (lds_u32(sB + wo) & bit) reds_and(sB + wo, ~bit); else reds_and(sA + wo, ~bit);
                 }
             }
             __syncwarp();
         }
-        const bool dup = doy_dup[d] != 0;
+        const bool dup = range_dup && doy_dup[d] != 0;
 
+        // members per lane slice (and the running count in front of every word), inclusive scan across lanes
         int s = 0;
-        if (!dup) {
-#pragma unroll 4
-            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]); }
-        } else {
-            for (int i = 0; i < wpl; i++) { pre[lane * wpl + i] = (uint16_t)s; s += __popc(A[lane * wpl + i]) + __popc(B[lane * wpl + i]); }
+        {
+            const uint32_t a0 = sA + 4u * (lane * wpl), b0 = sB + 4u * (lane * wpl), p0a = sPre + 2u * (lane * wpl);
+            if (!dup) {
+#pragma unroll 11
+                for (int i = 0; i < wpl; i++) { sts_u16(p0a + 2 * i, (uint32_t)s); s += __popc(lds_u32(a0 + 4 * i)); }
+            } else {
+                for (int i = 0; i < wpl; i++) { sts_u16(p0a + 2 * i, (uint32_t)s); s += __popc(lds_u32(a0 + 4 * i)) + __popc(lds_u32(b0 + 4 * i)); }
+            }
         }
         int incl = s;
 #pragma unroll
@@ -654,16 +699,15 @@ k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
         __syncwarp();
 
         int w_nan = 0, w_pinf = 0, w_ninf = 0;
-        if (nonfinite) {
+        if (nonfinite) {                                          // rare: count the window's non-finite members by rank range
             w_ninf = range_count(A, B, dup, wpl, lane, 0, n_ninf);
             w_pinf = range_count(A, B, dup, wpl, lane, E - n_nan - n_pinf, E - n_nan);
             w_nan = range_count(A, B, dup, wpl, lane, E - n_nan, E);
         }
 
-        for (int p0 = 0; p0 < P; p0 += 16) {
-            const int p = min(p0 + (lane >> 1), P - 1);
-            const int target = (lane & 1) ? sel.pos_hi[p] : sel.pos_lo[p];
-            int lo = 0, hi = 31;
+        for (int rnd = 0; rnd < n_rounds; rnd++) {
+            const int target = rnd ? tgt[1] : tgt[0];
+            int lo = 0, hi = 31;                                  // first lane whose inclusive count exceeds target
 #pragma unroll
             for (int it = 0; it < 5; it++) {
                 const int mid = (lo + hi) >> 1;
@@ -672,26 +716,28 @@ k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
             }
             const int owner = lo;
             int rem = target - (__shfl_sync(0xffffffffu, incl, owner) - __shfl_sync(0xffffffffu, s, owner));
-            const uint16_t *pw = pre + owner * wpl;
-            int wl = 0, wh = wpl - 1;
-            while (wl < wh) {
-                const int mid = (wl + wh + 1) >> 1;
-                if ((int)pw[mid] <= rem) wl = mid; else wh = mid - 1;
+            // last word of the owner's slice whose running count is <= rem
+            const uint32_t pw = sPre + 2u * (owner * wpl);
+            int wl = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int cand = wl + step;
+                if (step < 2 * wpl && cand < wpl && (int)lds_u16(pw + 2 * cand) <= rem) wl = cand;
             }
             const int w = owner * wpl + wl;
-            rem -= pw[wl];
-            const uint32_t a = A[w], b = dup ? B[w] : 0u;
+            rem -= (int)lds_u16(pw + 2 * wl);
+            const uint32_t a = lds_u32(sA + 4u * w), b = dup ? lds_u32(sB + 4u * w) : 0u;
             const int bitpos = dup ? select_in_word<true>(a, b, rem) : select_in_word<false>(a, 0u, rem);
             const int r = min(w * 32 + bitpos, E - 1);
             const float valf = V[r];
             const double lower = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2);
             const double upper = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2 + 1);
-            if (lane < 16 && p0 + lane < P) {
-                const int pp = p0 + lane, mode = sel.mode[pp];
+            if (lane < 16 && rnd * 16 + lane < P) {
+                const int pp = rnd * 16 + lane, mode = rnd ? md[1] : md[0];
                 const double nan = __longlong_as_double(0x7ff8000000000000LL);
                 double v;
                 if (mode == kSelInterp) {                         // arraymath.py:1697-1701
-                    v = __dadd_rn(__dmul_rn(lower, sel.w_lo[pp]), __dmul_rn(upper, sel.w_hi[pp]));
+                    v = __dadd_rn(__dmul_rn(lower, rnd ? w_lo[1] : w_lo[0]), __dmul_rn(upper, rnd ? w_hi[1] : w_hi[0]));
                 } else if (mode == kSelMax) {                     // arraymath.py:1669-1675
                     v = upper;
                     if ((w_pinf | w_ninf) && isinf(v)) v = nan;
@@ -781,7 +827,7 @@ static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, cons
         const size_t Epad = ((size_t)E + 63) & ~(size_t)63;
         const size_t need = Epad * 12 + (size_t)8 * kCellThreads * 4;
         const bool planes_fit = (size_t)pl.nwords_pad * (kCellWarps * 6 + n_b * 4) <= Epad * 8;
-        const bool ranks_fit = Epad * 2 <= (size_t)8 * kCellThreads * 4;
+        const bool ranks_fit = Epad * 2 + ((size_t)n_doy + 2 + pl.ops.size()) * 2 <= (size_t)8 * kCellThreads * 4 && pl.ops.size() < 65536;
         pl.smem_cell = (need <= 227 * 1024 - 1024 && planes_fit && ranks_fit) ? need : 0;
     }
     // positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
@@ -899,8 +945,8 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
             {
                 KernelTimer timer(kThrSort, st);
                 k_thr_cell<<<(unsigned)C, kCellThreads, plan.smem_cell, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
-                                                                            L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
-                                                                            plan.sel, P, d_out, L.fallback, L.fallback + 1);
+                                                                            L.op_off, L.ops, L.doy_dup, (int)plan.ops.size(), plan.dpw, plan.ept,
+                                                                            plan.nwords_pad, plan.sel, P, d_out, L.fallback, L.fallback + 1);
                 HDP_LAUNCH_CHECK();
             }
             // cells whose samples pile into one bucket (rare): a few persistent CTAs walk the device-side list

@@ -11,8 +11,10 @@
 //     val  = sorted[f-1] * (1-m) + sorted[f] * m
 // which is bit-identical to the reference (tests/test_gpu_parity.py compares at 0 ulp).
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -122,7 +124,8 @@ k_thr_generic(const float *__restrict__ temps, int64_t C, int64_t T_b, int64_t l
 }
 
 // ----------------------------------------------------------------------------------------------------
-// k_thr_ranked: the fast path.  One CTA per cell.
+// k_thr_ranked: one CTA per cell, full radix sort + sliding rank bitmaps.  The single-kernel path for shapes k_thr_seg
+// does not cover (windows wider than its segments, E <= 65535).
 //
 //   1. gather the cell's E = n_doy * n_y window elements (every slot of the reference's time_index table,
 //      -1 pads included: they are ordinary elements holding the last sample) into shared memory;
@@ -387,374 +390,461 @@ k_thr_ranked(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
 }
 
 // ----------------------------------------------------------------------------------------------------
-// k_thr_cell: the current fast path.  One CTA per cell, same plan as k_thr_ranked (order the cell's samples once,
-// slide a rank bitmap over the days of year) with a cheaper ordering stage:
+// k_thr_seg: the current fast path.  One WARP per (cell, SEGMENT of S consecutive days of year); the warps of a CTA
+// own neighbouring cells of the same segment.
 //
-//   1. gather the E = n_doy * n_y elements into shared memory (batched independent loads), find the finite
-//      min / max and count NaN / +inf / -inf;
-//   2. quantise every sample to a MONOTONE 16-bit bucket  b = 1 + trunc((v - vmin) * 65532 / (vmax - vmin))
-//      (float subtraction, multiplication and truncation are all monotone, so bucket order never contradicts
-//      value order; -inf -> 0, +inf -> 65534, NaN -> 65535) and pack (bucket << 16 | element) into ONE word;
-//   3. stable LSD radix sort of the packed words on the bucket: 4 passes of 4 bits instead of 8 passes over
-//      (key, element) pairs.  Digit counters are private per thread, two digits per 32-bit word, in an
-//      XOR-swizzled layout so that both the per-thread updates and the 64-byte-per-thread scan are free of
-//      bank conflicts;
-//   4. samples that share a bucket are adjacent now; each run is put in true order by its first owner thread
-//      (insertion sort on the exact float keys; runs are 1-3 long for real temperature data).  A cell whose
-//      samples pile into one bucket (an outlier stretching the range) is handed to k_thr_ranked through a
-//      device-side list instead;
-//   5./6. rank bitmaps and percentile selection exactly as in k_thr_ranked.
+// The windows of a segment touch R <= S + W - 1 day-of-year rows, i.e. NE = R * n_y <= 1024 samples.
+//   G. the CTA gathers the [cells x NE] tile: 8 neighbouring cells of one time step are one 32-byte sector, so every
+//      sector that crosses L2 -> SM is used completely (one block-wide barrier; everything after it is warp-private);
+//   1. each lane takes 32 of its cell's samples into registers; finite min / max, NaN / +inf / -inf counts;
+//   2. counting sort in ONE pass: monotone bucket b = 1 + trunc((v - vmin) * scale) out of 2048 (float subtraction,
+//      multiplication and truncation are monotone, so bucket order never contradicts value order; -inf, +inf and NaN
+//      have buckets of their own), one shared-memory atomic on a 16-bit counter claims the slot inside the bucket;
+//      the lane that draws slot 1 puts the bucket on a work list (it holds more than one sample);
+//   3. exclusive scan of the counters (two packed 16-bit sums per add), position = base[bucket] + slot;
+//   4. the samples are scattered to their positions together with their local row; buckets on the work list are
+//      put in exact order by insertion sort on the float values, long runs by a warp-wide counting rank;
+//   5. PB[i] = bitmap over the sorted positions ("local ranks") of the samples in local rows < i, and
+//      cum[i][w] = how many of them sit in words < w.  Rows own disjoint bits, so the members of a window of rows
+//      [r0, r1) are PB[r1] ^ PB[r0] and cum[r1][w] - cum[r0][w] of them come before word w;
+//   6. every (day of year, percentile) query is answered independently by one lane: binary search over the 32
+//      words, in-word select, value lookup, interpolation in double.  Rows pooled twice (the reference's mirrored
+//      year-end wrap) are a second set of ranges.
+// Each ordering serves S days x P percentiles; nothing a query reads changes once built.  Samples never leave the SM.
 // ----------------------------------------------------------------------------------------------------
-// 32-bit shared-state-space accesses: no generic -> shared conversion in front of every atomic
+// 32-bit shared-state-space accesses: no generic -> shared conversion in front of every access
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void reds_and(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t atoms_or(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 
-constexpr int kCellThreads = 1024;
-constexpr int kCellWarps = kCellThreads / 32;
-constexpr int kMaxTieRun = 48;
+constexpr int kSegWarps = 8;                                      // warps = cells per CTA: 8 x 4 bytes = one sector per time step
+constexpr int kSegCap = 1024;                                     // samples per segment: 32 words of 32 sorted positions
+constexpr int kSegRounds = kSegCap / 32;
+constexpr int kSegNB = 2048, kSegNBHalf = kSegNB / 2;             // buckets; 16-bit counters, bucket b -> word b & 1023, half b >> 10
+constexpr int kSegNBF = kSegNB - 4;                               // finite buckets 1 .. NBF; -inf 0, +inf NB-3, NaN NB-2
+constexpr int kSegRowsMax = 32;                                   // local rows 0 .. R of the prefix tables: R <= 31
+constexpr int kSegPst = 33, kSegCst = 34;                         // words per PB row, u16 per cum row (both odd in words)
+constexpr int kSegLongRun = 32;                                   // buckets with more samples are ordered by the whole warp
+constexpr int kSegRanges = 5;                                     // <= 3 ranges of rows pooled (at least) once + <= 2 pooled twice
+// per-warp workspace (bytes)
+constexpr int kSegOffSv = 0;                                      // f32 [1024] the gathered tile row, then the sorted values
+constexpr int kSegOffCnt = 4096;                                  // u32 [1024 + 32] packed counters / bases (word w at w + (w >> 5)), then PB [32][33]
+constexpr int kSegOffRw = kSegOffCnt + 4224;                      // u8 [1024] local row of every sorted position ...
+constexpr int kSegOffWl = kSegOffRw + 1024;                       // ... u16 [512] work list (then the row copy of a long run) ...
+constexpr int kSegOffLong = kSegOffWl + 1024;                     // ... u32 [32] long runs; the three together: cum u16 [32][34]
+constexpr int kSegWarpBytes = kSegOffLong + 128 + 16;             // = 16 (mod 128): the 8 tile rows start in different banks
+static_assert(kSegOffLong + 128 - kSegOffRw >= kSegRowsMax * kSegCst * 2, "cum does not fit");
+static_assert(kSegRowsMax * kSegPst * 4 <= 4224, "PB does not fit");
 
-__global__ void __launch_bounds__(kCellThreads, 1)
-k_thr_cell(const float *__restrict__ temps, int64_t T_b, int64_t ld_t,
-           const int *__restrict__ time_index, int E, int n_y, int n_doy, int n,
-           const int *__restrict__ op_off, const int *__restrict__ ops, const uint8_t *__restrict__ doy_dup,
-           int n_ops, int dpw, int ept, int nwords_pad, const __grid_constant__ SelTable sel, int P, double *__restrict__ out,
-           int *__restrict__ fallback_count, int *__restrict__ fallback_cells)
+struct SegGeom {
+    int S, n_seg;                       // days per segment, segments per cell
+    int gc, n_groups;                   // cell groups (of kSegWarps cells) per L2-sized chunk, cell groups in all
+    int ny_magic;                       // (k * ny_magic) >> 16 == k / n_y for k < 1024
+};
+
+struct SelShared {                      // SelTable without the k_thr_ranked bookkeeping, in shared memory
+    int pos_lo[HDP_B200_MAX_PERCENTILES], pos_hi[HDP_B200_MAX_PERCENTILES], mode[HDP_B200_MAX_PERCENTILES];
+    double w_lo[HDP_B200_MAX_PERCENTILES], w_hi[HDP_B200_MAX_PERCENTILES];
+};
+
+__device__ __forceinline__ uint32_t lowmask(uint32_t n) { return n >= 32u ? 0xffffffffu : ((1u << n) - 1u); }
+__device__ __forceinline__ uint32_t byte_of(const uint4 &v, int i)
 {
-    constexpr int NT = kCellThreads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Epad = (E + 63) & ~63;
-    float *x = (float *)smem_raw;                                 // samples by element
-    uint32_t *PA = (uint32_t *)(x + Epad);                        // packed (bucket << 16 | element), sorted at the end
-    uint32_t *PB = PA + Epad;                                     // second sort buffer; sorted VALUES afterwards
-    uint32_t *Wc = PB + Epad;                                     // [8][NT] digit counters (two digits per word), swizzled
-    float *V = (float *)PB;
-    uint16_t *rank_of = (uint16_t *)Wc;                           // after the sort
-    uint32_t *planes = (uint32_t *)x;                             // after the sort: bitmaps over x + PA
-    __shared__ int s_nonfinite[3];                                // NaN, +inf, -inf elements of this cell
-    __shared__ float s_min[kCellWarps], s_max[kCellWarps];
-    __shared__ uint32_t s_tot[kCellWarps];
-    __shared__ int s_fallback;
+    const uint32_t w = i < 4 ? v.x : i < 8 ? v.y : i < 12 ? v.z : v.w;
+    return (w >> ((i & 3) * 8)) & 0xffu;
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t c = blockIdx.x;
-
-    if (tid < 3) s_nonfinite[tid] = 0;
-    if (tid == 0) s_fallback = 0;
-    __syncthreads();
-
-    // ---- 1. gather (loads issued four at a time, independent of each other) ----
-    const float pinf = __int_as_float(0x7f800000);
-    float vmin = pinf, vmax = -pinf;
-    int c_nan = 0, c_pinf = 0, c_ninf = 0;
-    for (int e4 = tid; e4 < E; e4 += 4 * NT) {
-        int64_t t[4];
-        float v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int e = e4 + i * NT;
-            t[i] = e < E ? time_index[e] : 0;
-            if (t[i] < 0) t[i] += T_b;                            // -1 pads read the LAST sample (threshold.py:35,77)
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = temps[t[i] * ld_t + c];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int e = e4 + i * NT;
-            if (e < E) {
-                x[e] = v[i];
-                if (v[i] != v[i]) c_nan++;
-                else if (v[i] == pinf) c_pinf++;
-                else if (v[i] == -pinf) c_ninf++;
-                else { vmin = fminf(vmin, v[i]); vmax = fmaxf(vmax, v[i]); }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    }
-    c_nan = __reduce_add_sync(0xffffffffu, c_nan);
-    c_pinf = __reduce_add_sync(0xffffffffu, c_pinf);
-    c_ninf = __reduce_add_sync(0xffffffffu, c_ninf);
-    if (lane == 0) {
-        s_min[warp] = vmin; s_max[warp] = vmax;
-        if (c_nan) atomicAdd(&s_nonfinite[0], c_nan);
-        if (c_pinf) atomicAdd(&s_nonfinite[1], c_pinf);
-        if (c_ninf) atomicAdd(&s_nonfinite[2], c_ninf);
-    }
-    __syncthreads();
-    vmin = s_min[lane]; vmax = s_max[lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    }
-
-    // ---- 2. monotone 16-bit buckets, packed with the element index ----
-    const float range = vmax - vmin;
-    const float scale = (range > 0.0f && range < pinf) ? 65532.0f / range : 0.0f;
-    for (int e = tid; e < E; e += NT) {
-        const float v = x[e];
-        uint32_t b;
-        if (v != v) b = 65535u;
-        else if (v == pinf) b = 65534u;
-        else if (v == -pinf) b = 0u;
-        else b = 1u + (uint32_t)min(65532, max(0, __float2int_rz((v - vmin) * scale)));
-        PA[e] = (b << 16) | (uint32_t)e;
-    }
-    __syncthreads();
-
-    // ---- 3. stable LSD radix sort on the bucket: 4 passes x 4 bits ----
+// A window as row ranges over the segment's local rows: range k covers rows [lo_k, hi_k); ranges < n1 are the rows
+// pooled at least once, ranges n1 .. nr-1 the rows pooled twice.  ca/cb: shared addresses of cum rows hi/lo, pa/pb: of PB rows.
+template <int NR>
+struct SegWin {
+    uint32_t ca[NR], cb[NR], pa[NR], pb[NR];
+    int n1, nr;
+    __device__ __forceinline__ int before(int w) const            // members in words < w
     {
-        uint32_t *src = PA, *dst = PB;
-        const int e0 = min(tid * ept, E), e1 = min(e0 + ept, E);
-        // word of digit pair k of this thread: k * NT + tsw (16-byte pieces XOR-swizzled inside groups of 8)
-        const int tsw = ((((tid >> 2) ^ (warp & 7)) << 2) | (tid & 3));
-        for (int pass = 0; pass < 4; pass++) {
-            const int shift = 16 + 4 * pass;
+        int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) Wc[k * NT + tsw] = 0u;
-            // (no barrier needed: every thread only touches its own 8 words until the scan)
-            for (int e = e0; e < e1; e++) {
-                const uint32_t d = (src[e] >> shift) & 15u;
-                Wc[(d >> 1) * NT + tsw] += 1u << ((d & 1u) << 4);
+        for (int k = 0; k < NR; k++)
+            if (NR == 1 || k < nr) cnt += (int)lds_u16(ca[k] + 2u * w) - (int)lds_u16(cb[k] + 2u * w);
+        return cnt;
+    }
+    __device__ __forceinline__ void bits(int w, uint32_t &a, uint32_t &b) const   // a: members of word w, b: members pooled twice
+    {
+        a = 0u; b = 0u;
+#pragma unroll
+        for (int k = 0; k < NR; k++)
+            if (NR == 1 || k < nr) {
+                const uint32_t v = lds_u32(pa[k] + 4u * w) ^ lds_u32(pb[k] + 4u * w);
+                if (NR == 1 || k < n1) a |= v; else b |= v;
             }
-            __syncthreads();
-            // exclusive scan in (digit, thread) order.  Thread u < 512 owns 16 consecutive words of one digit pair
-            // (both halves): chunk u -> pair k = u >> 6, threads 16 * (u & 63) ... + 15.
-            uint32_t ex[16], run = 0u, incl = 0u;
-            uint4 *W4 = reinterpret_cast<uint4 *>(Wc);
-            const int sw = (tid >> 1) & 7;
-            if (tid < 512) {
+    }
+};
+
+// sorted positions of the pos_lo-th and pos_hi-th (0-based, pos_lo <= pos_hi < n) members of the window
+template <int NR>
+__device__ __forceinline__ void seg_pick(const SegWin<NR> &win, int pos_lo, int pos_hi, int &lr_lo, int &lr_hi)
+{
+    int w = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint4 q = W4[(4 * tid + j) ^ sw];
-                    ex[4 * j + 0] = q.x; ex[4 * j + 1] = q.y; ex[4 * j + 2] = q.z; ex[4 * j + 3] = q.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j++) { const uint32_t w = ex[j]; ex[j] = run; run += w; }   // packed lo | hi << 16
-                incl = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                if (lane == 31) s_tot[warp] = incl;
-            }
-            __syncthreads();
-            if (tid < 512) {
-                const int g0 = warp & ~1;                         // first warp of this digit pair
-                const uint32_t t = lane < 16 ? s_tot[lane] : 0u;
-                const uint32_t before = __reduce_add_sync(0xffffffffu, lane < g0 ? t : 0u);
-                const uint32_t t0 = __shfl_sync(0xffffffffu, t, g0), t1 = __shfl_sync(0xffffffffu, t, g0 + 1);
-                const uint32_t before_all = (before & 0xffffu) + (before >> 16);
-                const uint32_t grp = warp == g0 ? 0u : t0;        // warps of this pair in front of this one
-                const uint32_t exw = incl - run;                  // threads of this warp in front of this one
-                const uint32_t base_lo = before_all + (grp & 0xffffu) + (exw & 0xffffu);
-                const uint32_t base_hi = before_all + ((t0 + t1) & 0xffffu) + (grp >> 16) + (exw >> 16);
-#pragma unroll
-                for (int j = 0; j < 16; j++) ex[j] = (base_lo + (ex[j] & 0xffffu)) | ((base_hi + (ex[j] >> 16)) << 16);
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    W4[(4 * tid + j) ^ sw] = make_uint4(ex[4 * j + 0], ex[4 * j + 1], ex[4 * j + 2], ex[4 * j + 3]);
-            }
-            __syncthreads();
-            for (int e = e0; e < e1; e++) {
-                const uint32_t w = src[e];
-                const uint32_t d = (w >> shift) & 15u, sh = (d & 1u) << 4;
-                uint32_t *cw = &Wc[(d >> 1) * NT + tsw];
-                const uint32_t cv = *cw;
-                *cw = cv + (1u << sh);
-                dst[(cv >> sh) & 0xffffu] = w;
-            }
-            __syncthreads();
-            uint32_t *tp = src; src = dst; dst = tp;
+    for (int step = 16; step >= 1; step >>= 1)
+        if (win.before(w + step) <= pos_lo) w += step;
+    uint32_t a, b;
+    win.bits(w, a, b);
+    int rem = pos_lo - win.before(w);
+    lr_lo = w * 32 + (NR == 1 ? select_in_word<false>(a, 0u, rem) : select_in_word<true>(a, b, rem));
+    lr_hi = lr_lo;
+    if (pos_hi != pos_lo) {
+        rem += pos_hi - pos_lo;
+        int cw = __popc(a) + __popc(b);
+        while (rem >= cw && w < 31) {                             // the upper pick lives in a later word
+            rem -= cw;
+            w++;
+            win.bits(w, a, b);
+            cw = __popc(a) + __popc(b);
         }
-        // four passes: the sorted words are back in PA
+        lr_hi = w * 32 + (NR == 1 ? select_in_word<false>(a, 0u, rem) : select_in_word<true>(a, b, rem));
+    }
+}
 
-        // ---- 4. exact order inside runs of equal bucket ----
-        if (e0 < e1) {
-            uint32_t prev_b = e0 > 0 ? PA[e0 - 1] >> 16 : 0xffffffffu;
-            uint32_t w_cur = PA[e0];
-            for (int i = e0; i < e1; i++) {
-                const uint32_t b = w_cur >> 16;
-                const uint32_t w_next = i + 1 < E ? PA[i + 1] : 0xffffffffu;
-                const bool start = b != prev_b;
-                prev_b = b;
-                w_cur = w_next;
-                if (!start || (w_next >> 16) != b || i + 1 >= E) continue;   // not a run start, or a run of one
-                if (b == 0u || b >= 65534u) continue;             // -inf / +inf / NaN: identical keys
-                int j = i + 2;
-                while (j < E && (PA[j] >> 16) == b) j++;
-                if (j - i > kMaxTieRun) {                         // long run: fine if already ordered (ties), else hand over
-                    bool ordered = true;
-                    uint32_t kp = f32_to_key(x[PA[i] & 0xffffu]);
-                    for (int a = i + 1; a < j && ordered; a++) {
-                        const uint32_t ka = f32_to_key(x[PA[a] & 0xffffu]);
-                        ordered = ka >= kp;
-                        kp = ka;
-                    }
-                    if (!ordered) s_fallback = 1;
-                    continue;
-                }
-                for (int a = i + 1; a < j; a++) {
-                    const uint32_t wa = PA[a];
-                    const uint32_t ka = f32_to_key(x[wa & 0xffffu]);
-                    int bpos = a;
-                    while (bpos > i) {
-                        const uint32_t wb = PA[bpos - 1];
-                        if (f32_to_key(x[wb & 0xffffu]) <= ka) break;
-                        PA[bpos] = wb;
-                        bpos--;
-                    }
-                    PA[bpos] = wa;
-                }
-                if (i + 1 < e1) w_cur = PA[i + 1];                // the run was permuted: re-read the next word
-            }
+// members of the window at sorted positions < L
+template <int NR>
+__device__ __forceinline__ int seg_below(const SegWin<NR> &win, int L, int n)
+{
+    if (L >= kSegCap) return n;
+    uint32_t a, b;
+    win.bits(L >> 5, a, b);
+    const uint32_t m = lowmask((uint32_t)(L & 31));
+    return win.before(L >> 5) + __popc(a & m) + __popc(b & m);
+}
+
+// start of bucket b in the sorted order (after the scan)
+__device__ __forceinline__ int seg_bucket_base(uint32_t s_cnt, uint32_t b)
+{
+    const uint32_t w = b & (kSegNBHalf - 1);
+    return (int)((lds_u32(s_cnt + 4u * (w + (w >> 5))) >> ((b >> 6) & 16u)) & 0xffffu);
+}
+
+// phase 2 for one register round: bucket, slot, work list
+template <bool kNonFinite>
+__device__ __forceinline__ uint32_t seg_claim(float v, float vmin, float scale, bool valid, uint32_t s_cnt, uint32_t s_wl, uint32_t s_wlcount)
+{
+    const int bi = __float2int_rz((v - vmin) * scale);            // finite: >= 0; NaN -> 0
+    uint32_t b = 1u + (uint32_t)min(bi, kSegNBF - 1);
+    bool finite_bucket = true;
+    if (kNonFinite) {
+        const float pinf = __int_as_float(0x7f800000);
+        b = 1u + (uint32_t)min(max(bi, 0), kSegNBF - 1);
+        if (v == pinf) b = (uint32_t)kSegNB - 3u;
+        if (v == -pinf) b = 0u;
+        if (v != v) b = (uint32_t)kSegNB - 2u;
+        finite_bucket = b - 1u < (uint32_t)kSegNBF;
+    }
+    const uint32_t w = b & (kSegNBHalf - 1), sh = (b >> 6) & 16u;
+    uint32_t pk = 0u;
+    if (valid) {
+        const uint32_t slot = (atoms_add(s_cnt + 4u * (w + (w >> 5)), 1u << sh) >> sh) & 0xffffu;
+        pk = (b << 16) | slot;
+        if (slot == 1u && finite_bucket) sts_u16(s_wl + 2u * atoms_add(s_wlcount, 1u), b);
+    }
+    return pk;
+}
+
+__global__ void __launch_bounds__(kSegWarps * 32, 2)
+k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
+          const int *__restrict__ seg_time, const int *__restrict__ seg_ne, const uint4 *__restrict__ doy_rng,
+          const __grid_constant__ SegGeom geo, const __grid_constant__ SelTable sel, int P, int n, int n_doy,
+          double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SelShared s_sel;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // block -> (chunk of cell groups, segment, cell group): blocks in flight share the segment's time rows, and the
+    // halo rows a chunk's neighbouring segments read again are still in L2
+    const int per_chunk = geo.n_seg * geo.gc;
+    const int chunk = blockIdx.x / per_chunk, rem_b = blockIdx.x - chunk * per_chunk;
+    const int gcc = min(geo.gc, geo.n_groups - chunk * geo.gc);   // cell groups of this chunk
+    const int sg = rem_b / gcc, group = chunk * geo.gc + (rem_b - sg * gcc);
+    if (sg >= geo.n_seg) return;                                  // block-uniform (the last chunk is smaller), before any barrier
+    const int64_t c0 = (int64_t)group * kSegWarps;
+    const int NE = seg_ne[sg];
+
+    for (int i = tid; i < P; i += kSegWarps * 32) {
+        s_sel.pos_lo[i] = sel.pos_lo[i]; s_sel.pos_hi[i] = sel.pos_hi[i]; s_sel.mode[i] = sel.mode[i];
+        s_sel.w_lo[i] = sel.w_lo[i]; s_sel.w_hi[i] = sel.w_hi[i];
+    }
+    // ---- G. gather the [cells x NE] tile: lanes 8j .. 8j+7 read the 8 cells of one time step ----
+    {
+        const int *st = seg_time + (size_t)sg * kSegCap;
+        const int cl = tid & (kSegWarps - 1);
+        const float *src = temps + min(c0 + cl, C - 1);
+        float *dst = (float *)(smem_raw + (size_t)cl * kSegWarpBytes + kSegOffSv);
+#pragma unroll 4
+        for (int k = tid / kSegWarps; k < NE; k += 32) dst[k] = src[(int64_t)st[k] * ld_t];
+    }
+    __syncthreads();                                              // the only block-wide barrier
+    const int64_t cell = c0 + warp;
+    if (cell >= C) return;                                        // warp-uniform
+
+    const uint32_t s_base = smem_u32(smem_raw + (size_t)warp * kSegWarpBytes);
+    const uint32_t s_sv = s_base + kSegOffSv, s_cnt = s_base + kSegOffCnt, s_pb = s_cnt, s_rw = s_base + kSegOffRw,
+                   s_wl = s_base + kSegOffWl, s_long = s_base + kSegOffLong, s_cum = s_rw;
+    const uint32_t s_wlcount = s_long + 124u;                     // last word of the long-run list area
+
+    // ---- 1. samples into registers; min / max; non-finite census ----
+    const float pinf = __int_as_float(0x7f800000);
+    float x[kSegRounds];
+    float vmin = pinf, vmax = -pinf;
+    bool odd = false;                                             // some valid sample is NaN or +-inf
+#pragma unroll
+    for (int m = 0; m < kSegRounds; m++) {
+        x[m] = 0.0f;
+        if (32 * m < NE) {                                        // warp-uniform
+            const float v = lds_f32(s_sv + 4u * (32 * m + lane));
+            x[m] = v;
+            const bool valid = lane < NE - 32 * m;
+            odd |= valid && !(fabsf(v) < pinf);
+            if (valid) { vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
         }
     }
-    __syncthreads();
-    if (s_fallback) {                                             // block-uniform
-        if (tid == 0) fallback_cells[atomicAdd(fallback_count, 1)] = (int)c;
-        return;
-    }
-    uint16_t *s_opoff = rank_of + Epad;                           // [n_doy + 1] op offsets, then the ops (u16: row << 1 | enter)
-    uint16_t *s_ops = s_opoff + ((n_doy + 2) & ~1);
-    for (int r = tid; r < E; r += NT) {
-        const uint32_t idx = PA[r] & 0xffffu;
-        V[r] = x[idx];
-        rank_of[idx] = (uint16_t)r;
-    }
-    for (int i = tid; i <= n_doy; i += NT) s_opoff[i] = (uint16_t)op_off[i];
-    for (int i = tid; i < n_ops; i += NT) s_ops[i] = (uint16_t)ops[i];
-    __syncthreads();
-
-    // ---- 5./6. sliding rank bitmaps, one day-of-year range per warp (algorithm of k_thr_ranked; the tables live
-    //      in shared memory, shared-space addresses are 32-bit, per-lane selection constants are hoisted) ----
-    const int wpl = nwords_pad >> 5;
-    const bool range_dup = sel.b_slot[warp] >= 0;
-    const uint32_t sA = smem_u32(planes + (size_t)warp * nwords_pad);
-    const uint32_t sPre = smem_u32((uint16_t *)(planes + (size_t)kCellWarps * nwords_pad) + (size_t)warp * nwords_pad);
-    const uint32_t sB = smem_u32(planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad);
-    const uint32_t sRank = smem_u32(rank_of);
-    for (int i = lane; i < nwords_pad; i += 32) { sts_u32(sA + 4 * i, 0u); if (range_dup) sts_u32(sB + 4 * i, 0u); }
-    const int d_begin = warp * dpw, d_end = min(n_doy, d_begin + dpw);
-    const int n_nan = s_nonfinite[0], n_pinf = s_nonfinite[1], n_ninf = s_nonfinite[2];
-    const bool nonfinite = (n_nan | n_pinf | n_ninf) != 0;
-    const uint32_t *A = planes + (size_t)warp * nwords_pad;       // generic views for the rare non-finite bookkeeping
-    const uint32_t *B = planes + (size_t)kCellWarps * nwords_pad * 3 / 2 + (size_t)(range_dup ? sel.b_slot[warp] : 0) * nwords_pad;
-
-    // lane 2i -> lower pick of percentile i, lane 2i+1 -> upper pick; lanes 0..15 finish percentile `lane`
-    const int n_rounds = (P + 15) >> 4;
-    int tgt[2], md[2];
-    double w_lo[2], w_hi[2];
+    for (int i = lane; i < 1024 + 32; i += 32) sts_u32(s_cnt + 4u * i, 0u);
+    if (lane == 0) sts_u32(s_wlcount, 0u);
+    int n_nan = 0, n_pinf = 0, n_ninf = 0;
+    const bool nonfinite = __any_sync(0xffffffffu, odd);
+    if (nonfinite) {                                              // rare: redo min / max over the finite samples only, count the rest
+        vmin = pinf; vmax = -pinf;
 #pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-        const int p = min(rnd * 16 + (lane >> 1), P - 1), pp = min(rnd * 16 + (lane & 15), P - 1);
-        tgt[rnd] = (lane & 1) ? sel.pos_hi[p] : sel.pos_lo[p];
-        md[rnd] = sel.mode[pp]; w_lo[rnd] = sel.w_lo[pp]; w_hi[rnd] = sel.w_hi[pp];
+        for (int m = 0; m < kSegRounds; m++) {
+            const float v = x[m];
+            if (lane < NE - 32 * m) {
+                if (v != v) n_nan++;
+                else if (v == pinf) n_pinf++;
+                else if (v == -pinf) n_ninf++;
+                else { vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
+            }
+        }
+        n_nan = __reduce_add_sync(0xffffffffu, n_nan);
+        n_pinf = __reduce_add_sync(0xffffffffu, n_pinf);
+        n_ninf = __reduce_add_sync(0xffffffffu, n_ninf);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     __syncwarp();
 
-    int o1 = d_begin < d_end ? s_opoff[d_begin] : 0;
-    for (int d = d_begin; d < d_end; d++) {
-        // rows leaving / entering the window (multiset difference to the previous day; full build on the first)
-        const int o0 = o1;
-        o1 = s_opoff[d + 1];
-        for (int o = o0; o < o1; o++) {
-            const uint32_t op = s_ops[o], row = op >> 1;
-            for (int j = lane; j < n_y; j += 32) {
-                const uint32_t r = lds_u16(sRank + 2u * (row * n_y + j));
-                const uint32_t bit = 1u << (r & 31u), wo = (r >> 5) << 2;
-                if (!range_dup) {
-                    if (op & 1u) reds_or(sA + wo, bit); else reds_and(sA + wo, ~bit);
-                } else if (op & 1u) {
-                    if (atoms_or(sA + wo, bit) & bit) reds_or(sB + wo, bit);
-                } else {
-                    if (lds_u32(sB + wo) & bit) reds_and(sB + wo, ~bit); else reds_and(sA + wo, ~bit);
+    // ---- 2. monotone buckets; one atomic claims the slot inside the bucket ----
+    const float range = vmax - vmin;
+    const float scale = (range > 0.0f && range < pinf) ? (float)(kSegNBF - 1) / range : 0.0f;
+    uint32_t pk[kSegRounds];                                      // bucket << 16 | slot
+    if (!nonfinite) {
+#pragma unroll
+        for (int m = 0; m < kSegRounds; m++) {
+            pk[m] = 0u;
+            if (32 * m < NE) pk[m] = seg_claim<false>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, s_wlcount);
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < kSegRounds; m++) {
+            pk[m] = 0u;
+            if (32 * m < NE) pk[m] = seg_claim<true>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, s_wlcount);
+        }
+    }
+    __syncwarp();
+
+    // ---- 3. exclusive scan: lane l owns words 32 l .. 32 l + 31 (at 33 l + i); low halves = buckets < 1024 come first ----
+    {
+        const uint32_t a0 = s_cnt + 4u * (33u * lane);
+        uint32_t tot = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; i++) tot += lds_u32(a0 + 4u * i);     // two 16-bit sums per add: neither can carry (<= 1024)
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t carry = (incl - tot) + ((all & 0xffffu) << 16);      // high halves start after every low-half bucket
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const uint32_t wv = lds_u32(a0 + 4u * i);
+            sts_u32(a0 + 4u * i, carry);
+            carry += wv;
+        }
+    }
+    __syncwarp();
+
+    // ---- 4. scatter (value, local row) to the sorted position; exact order inside the work-list buckets ----
+#pragma unroll
+    for (int m = 0; m < kSegRounds; m++) {
+        if (32 * m < NE && lane < NE - 32 * m) {
+            const int pos = seg_bucket_base(s_cnt, pk[m] >> 16) + (int)(pk[m] & 0xffffu);
+            sts_f32(s_sv + 4u * pos, x[m]);
+            sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
+        }
+    }
+    __syncwarp();
+    {
+        const int n_wl = (int)lds_u32(s_wlcount);
+        int n_long = 0;
+        for (int q0 = 0; q0 < n_wl; q0 += 32) {
+            const int q = q0 + lane;
+            bool is_long = false;
+            uint32_t desc = 0u;
+            if (q < n_wl) {
+                const uint32_t b = lds_u16(s_wl + 2u * q);
+                const int i0 = seg_bucket_base(s_cnt, b), i1 = seg_bucket_base(s_cnt, b + 1u);
+                if (i1 - i0 > kSegLongRun) { is_long = true; desc = (uint32_t)i0 | ((uint32_t)i1 << 16); }
+                else {
+                    for (int a = i0 + 1; a < i1; a++) {
+                        const float ka = lds_f32(s_sv + 4u * a);
+                        const uint32_t ra = lds_u8(s_rw + a);
+                        int bpos = a;
+                        while (bpos > i0) {
+                            const float kb = lds_f32(s_sv + 4u * (bpos - 1));
+                            if (kb <= ka) break;
+                            sts_f32(s_sv + 4u * bpos, kb);
+                            sts_u8(s_rw + bpos, lds_u8(s_rw + bpos - 1));
+                            bpos--;
+                        }
+                        sts_f32(s_sv + 4u * bpos, ka);
+                        sts_u8(s_rw + bpos, ra);
+                    }
                 }
+            }
+            const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+            if (is_long) sts_u32(s_long + 4u * (n_long + __popc(lm & ((1u << lane) - 1u))), desc);   // <= 1024 / 33 = 31 long runs
+            n_long += __popc(lm);
+        }
+        __syncwarp();
+        // long runs (ties, fill values, an outlier squeezing the rest into one bucket): nothing to do when already in
+        // order, else a warp-wide counting rank through the (now dead) counter and work-list areas
+        for (int r = 0; r < n_long; r++) {
+            const uint32_t desc = lds_u32(s_long + 4u * r);
+            const int i0 = (int)(desc & 0xffffu), i1 = (int)(desc >> 16), L = i1 - i0;
+            bool bad = false;
+            for (int i = i0 + lane; i + 1 < i1; i += 32) bad |= lds_f32(s_sv + 4u * i) > lds_f32(s_sv + 4u * (i + 1));
+            if (!__any_sync(0xffffffffu, bad)) continue;
+            for (int i = lane; i < L; i += 32) {
+                const float vi = lds_f32(s_sv + 4u * (i0 + i));
+                int rank = 0;
+                for (int j = 0; j < L; j++) {
+                    const float vj = lds_f32(s_sv + 4u * (i0 + j));
+                    rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+                }
+                sts_f32(s_cnt + 4u * rank, vi);
+                sts_u8(s_wl + rank, lds_u8(s_rw + i0 + i));
+            }
+            __syncwarp();
+            for (int i = lane; i < L; i += 32) {
+                sts_f32(s_sv + 4u * (i0 + i), lds_f32(s_cnt + 4u * i));
+                sts_u8(s_rw + i0 + i, lds_u8(s_wl + i));
             }
             __syncwarp();
         }
-        const bool dup = range_dup && doy_dup[d] != 0;
+    }
+    __syncwarp();
 
-        // members per lane slice (and the running count in front of every word), inclusive scan across lanes
-        int s = 0;
-        {
-            const uint32_t a0 = sA + 4u * (lane * wpl), b0 = sB + 4u * (lane * wpl), p0a = sPre + 2u * (lane * wpl);
-            if (!dup) {
-#pragma unroll 11
-                for (int i = 0; i < wpl; i++) { sts_u16(p0a + 2 * i, (uint32_t)s); s += __popc(lds_u32(a0 + 4 * i)); }
-            } else {
-                for (int i = 0; i < wpl; i++) { sts_u16(p0a + 2 * i, (uint32_t)s); s += __popc(lds_u32(a0 + 4 * i)) + __popc(lds_u32(b0 + 4 * i)); }
+    // ---- 5. row bitmaps over the sorted positions -> PB (in place, lane = word) and cum (lane = row) ----
+    const int R = (NE * geo.ny_magic) >> 16;                      // rows of this segment (NE = R * n_y)
+    for (int i = lane; i < kSegRowsMax * kSegPst; i += 32) sts_u32(s_pb + 4u * i, 0u);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < kSegRounds; m++)
+        if (32 * m < NE && lane < NE - 32 * m)
+            reds_or(s_pb + 4u * (lds_u8(s_rw + 32 * m + lane) * kSegPst + m), 1u << lane);
+    __syncwarp();
+    {
+        uint32_t acc = 0u;
+        for (int i = 0; i < R; i++) {
+            const uint32_t a = s_pb + 4u * (i * kSegPst + lane), t = lds_u32(a);
+            sts_u32(a, acc);
+            acc |= t;
+        }
+        sts_u32(s_pb + 4u * (R * kSegPst + lane), acc);
+    }
+    __syncwarp();
+    if (lane <= R) {
+        uint32_t run = 0u;
+#pragma unroll 8
+        for (int w = 0; w < 32; w++) {
+            sts_u16(s_cum + 2u * (lane * kSegCst + w), run);
+            run += __popc(lds_u32(s_pb + 4u * (lane * kSegPst + w)));
+        }
+    }
+    __syncwarp();
+
+    // ---- 6. queries: one (day of the segment, percentile) per lane ----
+    const int L_ninf = n_ninf, L_fin = NE - n_nan - n_pinf, L_pinf = NE - n_nan;   // where the finite / +inf / NaN samples begin
+    const int d0 = sg * geo.S, nd = min(n_doy, d0 + geo.S) - d0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int qi = lane; qi < nd * P; qi += 32) {
+        const int dl = qi / P, p = qi - dl * P, d = d0 + dl;
+        const uint4 rg = doy_rng[d];
+        const int n1 = (int)byte_of(rg, 0), n2 = (int)byte_of(rg, 1);
+        const int pos_lo = s_sel.pos_lo[p], pos_hi = s_sel.pos_hi[p], mode = s_sel.mode[p];
+        int lr_lo, lr_hi, w_nan = 0, w_pinf = 0, w_ninf = 0;
+        if (n1 == 1 && n2 == 0) {                                 // one contiguous run of rows, each pooled once (almost every day)
+            SegWin<1> win;
+            const uint32_t r0 = byte_of(rg, 2), r1 = byte_of(rg, 5);
+            win.ca[0] = s_cum + 2u * (r1 * kSegCst); win.cb[0] = s_cum + 2u * (r0 * kSegCst);
+            win.pa[0] = s_pb + 4u * (r1 * kSegPst); win.pb[0] = s_pb + 4u * (r0 * kSegPst);
+            win.n1 = 1; win.nr = 1;
+            seg_pick<1>(win, pos_lo, pos_hi, lr_lo, lr_hi);
+            if (nonfinite) {
+                const int b_pinf = seg_below<1>(win, L_pinf, n);
+                w_ninf = seg_below<1>(win, L_ninf, n);
+                w_pinf = b_pinf - seg_below<1>(win, L_fin, n);
+                w_nan = n - b_pinf;
+            }
+        } else {
+            SegWin<kSegRanges> win;
+            win.n1 = n1; win.nr = n1 + n2;
+#pragma unroll
+            for (int k = 0; k < kSegRanges; k++) {
+                // slot k: k < n1 -> bytes 2+k / 5+k, else the (k - n1)-th pooled-twice range -> bytes 8+.. / 10+..
+                uint32_t r0 = 0u, r1 = 0u;
+#pragma unroll
+                for (int j = 0; j < 3; j++) if (k == j && j < n1) { r0 = byte_of(rg, 2 + j); r1 = byte_of(rg, 5 + j); }
+#pragma unroll
+                for (int j = 0; j < 2; j++) if (k == n1 + j && j < n2) { r0 = byte_of(rg, 8 + j); r1 = byte_of(rg, 10 + j); }
+                win.ca[k] = s_cum + 2u * (r1 * kSegCst); win.cb[k] = s_cum + 2u * (r0 * kSegCst);
+                win.pa[k] = s_pb + 4u * (r1 * kSegPst); win.pb[k] = s_pb + 4u * (r0 * kSegPst);
+            }
+            seg_pick<kSegRanges>(win, pos_lo, pos_hi, lr_lo, lr_hi);
+            if (nonfinite) {
+                const int b_pinf = seg_below<kSegRanges>(win, L_pinf, n);
+                w_ninf = seg_below<kSegRanges>(win, L_ninf, n);
+                w_pinf = b_pinf - seg_below<kSegRanges>(win, L_fin, n);
+                w_nan = n - b_pinf;
             }
         }
-        int incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        __syncwarp();
-
-        int w_nan = 0, w_pinf = 0, w_ninf = 0;
-        if (nonfinite) {                                          // rare: count the window's non-finite members by rank range
-            w_ninf = range_count(A, B, dup, wpl, lane, 0, n_ninf);
-            w_pinf = range_count(A, B, dup, wpl, lane, E - n_nan - n_pinf, E - n_nan);
-            w_nan = range_count(A, B, dup, wpl, lane, E - n_nan, E);
-        }
-
-        for (int rnd = 0; rnd < n_rounds; rnd++) {
-            const int target = rnd ? tgt[1] : tgt[0];
-            int lo = 0, hi = 31;                                  // first lane whose inclusive count exceeds target
-#pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const int mid = (lo + hi) >> 1;
-                const int v = __shfl_sync(0xffffffffu, incl, mid);
-                if (v > target) hi = mid; else lo = mid + 1;
-            }
-            const int owner = lo;
-            int rem = target - (__shfl_sync(0xffffffffu, incl, owner) - __shfl_sync(0xffffffffu, s, owner));
-            // last word of the owner's slice whose running count is <= rem
-            const uint32_t pw = sPre + 2u * (owner * wpl);
-            int wl = 0;
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const int cand = wl + step;
-                if (step < 2 * wpl && cand < wpl && (int)lds_u16(pw + 2 * cand) <= rem) wl = cand;
-            }
-            const int w = owner * wpl + wl;
-            rem -= (int)lds_u16(pw + 2 * wl);
-            const uint32_t a = lds_u32(sA + 4u * w), b = dup ? lds_u32(sB + 4u * w) : 0u;
-            const int bitpos = dup ? select_in_word<true>(a, b, rem) : select_in_word<false>(a, 0u, rem);
-            const int r = min(w * 32 + bitpos, E - 1);
-            const float valf = V[r];
-            const double lower = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2);
-            const double upper = (double)__shfl_sync(0xffffffffu, valf, (lane & 15) * 2 + 1);
-            if (lane < 16 && rnd * 16 + lane < P) {
-                const int pp = rnd * 16 + lane, mode = rnd ? md[1] : md[0];
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                double v;
-                if (mode == kSelInterp) {                         // arraymath.py:1697-1701
-                    v = __dadd_rn(__dmul_rn(lower, rnd ? w_lo[1] : w_lo[0]), __dmul_rn(upper, rnd ? w_hi[1] : w_hi[0]));
-                } else if (mode == kSelMax) {                     // arraymath.py:1669-1675
-                    v = upper;
-                    if ((w_pinf | w_ninf) && isinf(v)) v = nan;
-                } else {                                          // arraymath.py:1678-1695
-                    v = lower;
-                    if (w_pinf | w_ninf) {
-                        const int n_fin = n - (w_pinf + w_ninf);
-                        if (n_fin == 0) v = nan;
-                        if (w_pinf == 1 && n == 2) v = nan;
-                        if (w_ninf > 1) v = nan;
-                        if (n_fin == 1 && w_pinf > 1 && w_ninf != 1) v = nan;
-                    }
-                }
-                if (w_nan > 0) v = nan;                           // _can_collect_percentiles, arraymath.py:1714
-                out[(c * n_doy + d) * (int64_t)P + pp] = v;
+        const double lower = (double)lds_f32(s_sv + 4u * lr_lo), upper = (double)lds_f32(s_sv + 4u * lr_hi);
+        double v;
+        if (mode == kSelInterp) {                                 // arraymath.py:1697-1701
+            v = __dadd_rn(__dmul_rn(lower, s_sel.w_lo[p]), __dmul_rn(upper, s_sel.w_hi[p]));
+        } else if (mode == kSelMax) {                             // arraymath.py:1669-1675
+            v = upper;
+            if ((w_pinf | w_ninf) && isinf(v)) v = nan;
+        } else {                                                  // arraymath.py:1678-1695
+            v = lower;
+            if (w_pinf | w_ninf) {
+                const int n_fin = n - (w_pinf + w_ninf);
+                if (n_fin == 0) v = nan;
+                if (w_pinf == 1 && n == 2) v = nan;
+                if (w_ninf > 1) v = nan;
+                if (n_fin == 1 && w_pinf > 1 && w_ninf != 1) v = nan;
             }
         }
+        if (w_nan > 0) v = nan;                                   // _can_collect_percentiles, arraymath.py:1714
+        out[(cell * n_doy + d) * (int64_t)P + p] = v;
     }
 }
 
@@ -763,14 +853,13 @@ static bool bad_dims(int64_t C, int64_t T_b, int n_doy, int n_y, int W, int P)
     return C < 0 || T_b < 0 || n_doy <= 0 || n_y <= 0 || W <= 0 || P <= 0 || T_b > 0x3fffffff;
 }
 
-// What the fast path needs besides the reference's two tables.
+// What k_thr_ranked needs besides the reference's two tables.
 struct RankedPlan {
     bool usable = false;
     std::vector<int> op_off, ops;       // per day of year: (row << 1 | enter) ops relative to the previous day of the warp's range
     std::vector<uint8_t> doy_dup;       // window pools some row twice
     int dpw = 0, ept = 0, nwords_pad = 0;
     size_t smem = 0;
-    size_t smem_cell = 0;               // k_thr_cell (0 = its bitmaps do not fit: use k_thr_ranked for every cell)
     SelTable sel;
 };
 
@@ -778,6 +867,33 @@ static size_t ranked_smem(int E)
 {
     const size_t Epad = ((size_t)E + 63) & ~(size_t)63;
     return Epad * (4 + 2 + 4 + 2) + (size_t)kRadixBins * kRankedThreads * 2;
+}
+
+// positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
+static void fill_sel(SelTable &sel, int64_t n, const double *q, int P)
+{
+    for (int p = 0; p < HDP_B200_MAX_PERCENTILES; p++) {
+        sel.pos_lo[p] = sel.pos_hi[p] = 0;
+        sel.mode[p] = kSelInterp;
+        sel.w_lo[p] = sel.w_hi[p] = 0.0;
+        if (p >= P) continue;
+        volatile double pct = q[p] * 100.0;
+        if (pct == 100.0) { sel.mode[p] = kSelMax; sel.pos_lo[p] = sel.pos_hi[p] = (int)n - 1; continue; }
+        if (pct == 0.0) { sel.mode[p] = kSelMin; continue; }
+        volatile double frac = pct / 100.0;
+        volatile double scaled = (double)(n - 1) * frac;
+        volatile double rank = 1.0 + scaled;
+        const double f = floor(rank);
+        volatile double m = rank - f;
+        volatile double w0 = 1.0 - m;
+        int64_t k = (int64_t)f - 1;
+        if (k < 0) k = 0;
+        if (k >= n - 1) { sel.pos_lo[p] = sel.pos_hi[p] = (int)n - 1; }
+        else { sel.pos_lo[p] = (int)k; sel.pos_hi[p] = (int)k + 1; }
+        sel.w_lo[p] = w0;
+        sel.w_hi[p] = m;
+    }
+    for (int w = 0; w < 64; w++) sel.b_slot[w] = -1;
 }
 
 static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, const double *q, int P, RankedPlan &pl)
@@ -815,52 +931,123 @@ static void plan_ranked(const int32_t *win_rows, int n_doy, int n_y, int W, cons
         prev.swap(cur);
     }
     pl.op_off[n_doy] = (int)pl.ops.size();
+    fill_sel(pl.sel, n, q, P);
     int n_b = 0;
     for (int w = 0; w < 64; w++) {
-        pl.sel.b_slot[w] = -1;
         bool need = false;
         for (int d = w * pl.dpw; d < std::min(n_doy, (w + 1) * pl.dpw); d++) need |= pl.doy_dup[d] != 0;
         if (need && w < kRankedWarps) pl.sel.b_slot[w] = (int8_t)n_b++;
     }
     if ((size_t)pl.nwords_pad * (kRankedWarps * 6 + n_b * 4) > pl.smem - (((size_t)E + 63) & ~(size_t)63) * 6) return;
-    {
-        const size_t Epad = ((size_t)E + 63) & ~(size_t)63;
-        const size_t need = Epad * 12 + (size_t)8 * kCellThreads * 4;
-        const bool planes_fit = (size_t)pl.nwords_pad * (kCellWarps * 6 + n_b * 4) <= Epad * 8;
-        const bool ranks_fit = Epad * 2 + ((size_t)n_doy + 2 + pl.ops.size()) * 2 <= (size_t)8 * kCellThreads * 4 && pl.ops.size() < 65536;
-        pl.smem_cell = (need <= 227 * 1024 - 1024 && planes_fit && ranks_fit) ? need : 0;
-    }
-    // positions and weights: numba/np/arraymath.py:1655-1704 with n fixed (every window pools W * n_y samples)
-    for (int p = 0; p < HDP_B200_MAX_PERCENTILES; p++) {
-        pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = 0;
-        pl.sel.mode[p] = kSelInterp;
-        pl.sel.w_lo[p] = pl.sel.w_hi[p] = 0.0;
-        if (p >= P) continue;
-        volatile double pct = q[p] * 100.0;
-        if (pct == 100.0) { pl.sel.mode[p] = kSelMax; pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = (int)n - 1; continue; }
-        if (pct == 0.0) { pl.sel.mode[p] = kSelMin; continue; }
-        volatile double frac = pct / 100.0;
-        volatile double scaled = (double)(n - 1) * frac;
-        volatile double rank = 1.0 + scaled;
-        const double f = floor(rank);
-        volatile double m = rank - f;
-        volatile double w0 = 1.0 - m;
-        int64_t k = (int64_t)f - 1;
-        if (k < 0) k = 0;
-        if (k >= n - 1) { pl.sel.pos_lo[p] = pl.sel.pos_hi[p] = (int)n - 1; }
-        else { pl.sel.pos_lo[p] = (int)k; pl.sel.pos_hi[p] = (int)k + 1; }
-        pl.sel.w_lo[p] = w0;
-        pl.sel.w_hi[p] = m;
-    }
     pl.usable = true;
+}
+
+// ---- the segment path (k_thr_seg) ----
+struct SegPlan {
+    bool usable = false;
+    SegGeom geo;
+    std::vector<int> seg_time;          // [n_seg][kSegCap] time index of every sample slot (local row major), pads resolved
+    std::vector<int> seg_ne;            // [n_seg] samples per segment = rows * n_y
+    std::vector<uint8_t> doy_rng;       // [n_doy][16]: n1, n2, lo[3], hi[3], lo2[2], hi2[2] in local rows of the day's segment
+};
+
+static bool plan_seg_try(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, int n_doy, int n_y, int W, int S, SegPlan &sp)
+{
+    const int n_seg = (n_doy + S - 1) / S;
+    sp.seg_time.assign((size_t)n_seg * kSegCap, 0);
+    sp.seg_ne.assign(n_seg, 0);
+    sp.doy_rng.assign((size_t)n_doy * 16, 0);
+    std::vector<int> present(n_doy), loc(n_doy), mult;
+    for (int sg = 0; sg < n_seg; sg++) {
+        const int d0 = sg * S, d1 = std::min(n_doy, d0 + S);
+        std::fill(present.begin(), present.end(), 0);
+        for (int d = d0; d < d1; d++)
+            for (int k = 0; k < W; k++) present[win_rows[d * W + k]] = 1;
+        std::vector<int> r;
+        for (int i = 0; i < n_doy; i++) if (present[i]) r.push_back(i);
+        const int m = (int)r.size();
+        if (m + 1 > kSegRowsMax || (int64_t)m * n_y > kSegCap) return false;
+        // start the local order after the widest circular gap: a window is then a few runs of consecutive local rows
+        int start = 0, best = -1;
+        for (int i = 0; i < m; i++) {
+            const int gap = m == 1 ? n_doy : (r[(i + 1) % m] - r[i] + n_doy) % n_doy;
+            if (gap > best) { best = gap; start = (i + 1) % m; }
+        }
+        for (int k = 0; k < m; k++) {
+            const int row = r[(start + k) % m];
+            loc[row] = k;
+            for (int j = 0; j < n_y; j++) {
+                int64_t t = time_index[(size_t)row * n_y + j];
+                if (t < 0) t += T_b;                                        // -1 pads read the LAST sample (threshold.py:35,77)
+                sp.seg_time[(size_t)sg * kSegCap + (size_t)k * n_y + j] = (int)t;
+            }
+        }
+        sp.seg_ne[sg] = m * n_y;
+        for (int d = d0; d < d1; d++) {
+            mult.assign(m + 1, 0);
+            for (int k = 0; k < W; k++) mult[loc[win_rows[d * W + k]]]++;
+            uint8_t *g = &sp.doy_rng[(size_t)d * 16];
+            int n1 = 0, n2 = 0;
+            for (int k = 0; k < m; k++) {
+                if (mult[k] > 2) return false;                              // pooled more than twice: not this path
+                if (mult[k] >= 1 && (k == 0 || mult[k - 1] == 0)) {         // a run of rows pooled at least once starts
+                    if (n1 == 3) return false;
+                    int e = k;
+                    while (e < m && mult[e] >= 1) e++;
+                    g[2 + n1] = (uint8_t)k; g[5 + n1] = (uint8_t)e; n1++;
+                }
+                if (mult[k] == 2 && (k == 0 || mult[k - 1] != 2)) {         // a run of rows pooled twice starts
+                    if (n2 == 2) return false;
+                    int e = k;
+                    while (e < m && mult[e] == 2) e++;
+                    g[8 + n2] = (uint8_t)k; g[10 + n2] = (uint8_t)e; n2++;
+                }
+            }
+            g[0] = (uint8_t)n1; g[1] = (uint8_t)n2;
+        }
+    }
+    sp.geo.S = S; sp.geo.n_seg = n_seg;
+    return true;
+}
+
+static void plan_seg(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, int n_doy, int n_y, int W, SegPlan &sp)
+{
+    sp.usable = false;
+    if ((int64_t)W * n_y < 2 || n_y > kSegCap) return;
+    const int magic = (65536 + n_y - 1) / n_y;
+    for (int k = 0; k <= kSegCap; k++)
+        if (((k * magic) >> 16) != k / n_y) return;                         // the kernel divides sample slots by n_y with one multiply
+    // the largest S that fits: the ordering of a segment is shared by S days
+    for (int S = std::min(n_doy, kSegRowsMax); S >= 1; S--) {
+        if (2 * S < W - 1) return;                                          // more than 3x halo: k_thr_ranked does better
+        if (!plan_seg_try(time_index, win_rows, T_b, n_doy, n_y, W, S, sp)) continue;
+        sp.geo.ny_magic = magic;
+        sp.usable = true;
+        return;
+    }
+}
+
+static int thr_chunk_groups(int64_t T_b)
+{
+    // cell groups per chunk: the chunk's slab of the measure array (T_b x 8 cells x 4 bytes per group) should stay in L2, so that
+    // the halo rows neighbouring segments read again do not come from HBM twice; HDP_B200_THR_CHUNK_GROUPS overrides
+    static int forced = -1;
+    if (forced < 0) {
+        const char *s = getenv("HDP_B200_THR_CHUNK_GROUPS");
+        forced = s ? atoi(s) : 0;
+    }
+    if (forced > 0) return forced;
+    int64_t g = ((int64_t)56 << 20) / std::max<int64_t>(1, T_b * kSegWarps * 4);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, 1 << 20));
 }
 
 struct ThrLayout {
     size_t total = 0;
     float *xn = nullptr;
     int *time_index = nullptr, *win_rows = nullptr, *op_off = nullptr, *ops = nullptr;
-    int *fallback = nullptr;            // [1 + C]: count, then the cells k_thr_cell hands over to k_thr_ranked
     uint8_t *doy_dup = nullptr;
+    int *seg_time = nullptr, *seg_ne = nullptr;      // k_thr_seg tables
+    uint8_t *doy_rng = nullptr;
 };
 
 static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_norm, int n_doy, int n_y, int W)
@@ -873,12 +1060,14 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.op_off = cv.take<int>((size_t)n_doy + 1);
     L.ops = cv.take<int>((size_t)2 * W * (n_doy + kRankedWarps));           // <= 2W changes per day, W per range start
     L.doy_dup = cv.take<uint8_t>((size_t)n_doy);
-    L.fallback = cv.take<int>((size_t)C + 1);
+    L.seg_time = cv.take<int>((size_t)n_doy * kSegCap);                     // <= n_doy segments
+    L.seg_ne = cv.take<int>((size_t)n_doy);
+    L.doy_rng = cv.take<uint8_t>((size_t)n_doy * 16);
     L.total = cv.off;
     return L;
 }
 
-static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_cell
+static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
 static int g_force_ranked = 0;
 
 }  // namespace hdp
@@ -932,34 +1121,59 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
     }
     HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
 
-    RankedPlan plan;
-    if (!g_force_generic) plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, plan);
-    if (plan.usable) {
+    // plans depend on the tables only: keep the last one (calls are serialised on the host side; the launches are asynchronous)
+    static std::mutex plan_mu;
+    std::lock_guard<std::mutex> plan_lock(plan_mu);
+    static std::vector<int32_t> cached_rows, cached_ti;
+    static std::vector<double> cached_q;
+    static int64_t cached_dims[4] = {0, 0, 0, 0};
+    static RankedPlan plan;
+    static SegPlan seg;
+    const size_t n_ti = (size_t)n_doy * n_y, n_wr = (size_t)n_doy * W;
+    const bool same = cached_dims[0] == n_doy && cached_dims[1] == n_y && cached_dims[2] == W && cached_dims[3] == T_b &&
+                      cached_rows.size() == n_wr && std::equal(cached_rows.begin(), cached_rows.end(), h_win_rows) &&
+                      cached_ti.size() == n_ti && std::equal(cached_ti.begin(), cached_ti.end(), h_time_index) &&
+                      cached_q.size() == (size_t)P && std::equal(cached_q.begin(), cached_q.end(), h_q);
+    if (!same) {
+        plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, plan);
+        plan_seg(h_time_index, h_win_rows, T_b, n_doy, n_y, W, seg);
+        cached_rows.assign(h_win_rows, h_win_rows + n_wr);
+        cached_ti.assign(h_time_index, h_time_index + n_ti);
+        cached_q.assign(h_q, h_q + P);
+        cached_dims[0] = n_doy; cached_dims[1] = n_y; cached_dims[2] = W; cached_dims[3] = T_b;
+    }
+    const int E = n_doy * n_y;
+    if (seg.usable && !g_force_generic && !g_force_ranked) {
+        SelTable sel;
+        fill_sel(sel, b, h_q, P);
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_time, seg.seg_time.data(), sizeof(int) * seg.seg_time.size(), cudaMemcpyHostToDevice, st));
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_ne, seg.seg_ne.data(), sizeof(int) * seg.seg_ne.size(), cudaMemcpyHostToDevice, st));
+        HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_rng, seg.doy_rng.data(), seg.doy_rng.size(), cudaMemcpyHostToDevice, st));
+        static bool attr_done = false;
+        const size_t smem = (size_t)kSegWarps * kSegWarpBytes;
+        if (!attr_done) {
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        SegGeom geo = seg.geo;
+        geo.n_groups = (int)((C + kSegWarps - 1) / kSegWarps);
+        geo.gc = std::min(thr_chunk_groups(T_b), geo.n_groups);
+        const int64_t n_chunks = (geo.n_groups + geo.gc - 1) / geo.gc;
+        const int64_t blocks = n_chunks * geo.n_seg * geo.gc;
+        if (blocks > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
+        KernelTimer timer(kThrSeg, st);
+        k_thr_seg<<<(unsigned)blocks, kSegWarps * 32, smem, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel, P,
+                                                                  (int)b, n_doy, d_out);
+        HDP_LAUNCH_CHECK();
+        return HDP_B200_OK;
+    }
+    if (plan.usable && !g_force_generic) {
         HDP_CUDA_TRY(cudaMemcpyAsync(L.op_off, plan.op_off.data(), sizeof(int) * plan.op_off.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_dup, plan.doy_dup.data(), plan.doy_dup.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        if (plan.smem_cell && !g_force_ranked) {
-            HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_cell));
-            HDP_CUDA_TRY(cudaMemsetAsync(L.fallback, 0, sizeof(int), st));
-            {
-                KernelTimer timer(kThrSort, st);
-                k_thr_cell<<<(unsigned)C, kCellThreads, plan.smem_cell, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
-                                                                            L.op_off, L.ops, L.doy_dup, (int)plan.ops.size(), plan.dpw, plan.ept,
-                                                                            plan.nwords_pad, plan.sel, P, d_out, L.fallback, L.fallback + 1);
-                HDP_LAUNCH_CHECK();
-            }
-            // cells whose samples pile into one bucket (rare): a few persistent CTAs walk the device-side list
-            KernelTimer timer(kThrSelect, st);
-            const unsigned grid = (unsigned)std::min<int64_t>(C, 148);
-            k_thr_ranked<<<grid, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
-                                                                 L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
-                                                                 plan.sel, P, d_out, L.fallback, L.fallback + 1);
-            HDP_LAUNCH_CHECK();
-            return HDP_B200_OK;
-        }
-        KernelTimer timer(kThrSort, st);
-        k_thr_ranked<<<(unsigned)C, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, n_doy * n_y, n_y, n_doy, (int)b,
+        KernelTimer timer(kThrRanked, st);
+        k_thr_ranked<<<(unsigned)C, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, E, n_y, n_doy, (int)b,
                                                                     L.op_off, L.ops, L.doy_dup, plan.dpw, plan.ept, plan.nwords_pad,
                                                                     plan.sel, P, d_out, nullptr, nullptr);
         HDP_LAUNCH_CHECK();

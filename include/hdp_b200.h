@@ -141,8 +141,8 @@ int64_t hdp_b200_launch_count(void);
 #define HDP_B200_KERNEL_HOT_WORDS    3
 #define HDP_B200_KERNEL_SCAN         4
 #define HDP_B200_KERNEL_UNPACK_MASK  5
-#define HDP_B200_KERNEL_THR_SORT     6
-#define HDP_B200_KERNEL_THR_SELECT   7
+#define HDP_B200_KERNEL_THR_SEG      6   /* k_thr_seg */
+#define HDP_B200_KERNEL_THR_RANKED   7   /* k_thr_ranked */
 void hdp_b200_timing_enable(int on);
 int  hdp_b200_timing_read(int *ids, float *ms, int cap);
 

@@ -32,12 +32,12 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
-@pytest.fixture(params=["cell", "ranked", "generic"])
+@pytest.fixture(params=["seg", "ranked", "generic"])
 def thr_path(request, core):
-    """All three threshold kernels: the fast path (k_thr_cell, which hands badly conditioned cells to k_thr_ranked),
-    k_thr_ranked for every cell, and the generic gather+sort fallback."""
+    """All three threshold paths: the fast pair (k_thr_order + k_thr_segsel, which hands badly conditioned cells to
+    k_thr_ranked), k_thr_ranked for every cell, and the generic gather+sort fallback."""
     from hdp_b200 import _lib
-    _lib.lib().hdp_b200_thresholds_force_generic({"cell": 0, "generic": 1, "ranked": 2}[request.param])
+    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2}[request.param])
     yield request.param
     _lib.lib().hdp_b200_thresholds_force_generic(0)
 

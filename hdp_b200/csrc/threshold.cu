@@ -492,16 +492,25 @@ struct SegWin {
 template <int NR>
 __device__ __forceinline__ void seg_pick(const SegWin<NR> &win, int pos_lo, int pos_hi, int &lr_lo, int &lr_hi)
 {
-    int w = 0;
+    int w = 0, bw = 0;                                            // bw = members in words < w
 #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1)
-        if (win.before(w + step) <= pos_lo) w += step;
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int c = win.before(w + step);
+        if (c <= pos_lo) { w += step; bw = c; }
+    }
     uint32_t a, b;
     win.bits(w, a, b);
-    int rem = pos_lo - win.before(w);
-    lr_lo = w * 32 + (NR == 1 ? select_in_word<false>(a, 0u, rem) : select_in_word<true>(a, b, rem));
+    int rem = pos_lo - bw;
+    const int bit = NR == 1 ? select_in_word<false>(a, 0u, rem) : select_in_word<true>(a, b, rem);
+    lr_lo = w * 32 + bit;
     lr_hi = lr_lo;
     if (pos_hi != pos_lo) {
+        if (NR == 1 && pos_hi == pos_lo + 1) {                    // the next member: the next set bit, here or in a later word
+            a &= 0xfffffffeu << bit;
+            while (a == 0u && w < 31) { w++; win.bits(w, a, b); }
+            lr_hi = w * 32 + __ffs(a) - 1;
+            return;
+        }
         rem += pos_hi - pos_lo;
         int cw = __popc(a) + __popc(b);
         while (rem >= cw && w < 31) {                             // the upper pick lives in a later word
@@ -532,9 +541,9 @@ __device__ __forceinline__ int seg_bucket_base(uint32_t s_cnt, uint32_t b)
     return (int)((lds_u32(s_cnt + 4u * (w + (w >> 5))) >> ((b >> 6) & 16u)) & 0xffffu);
 }
 
-// phase 2 for one register round: bucket, slot, work list
+// phase 2 for one register round: bucket, slot; the lanes that draw slot 1 append their bucket to the work list
 template <bool kNonFinite>
-__device__ __forceinline__ uint32_t seg_claim(float v, float vmin, float scale, bool valid, uint32_t s_cnt, uint32_t s_wl, uint32_t s_wlcount)
+__device__ __forceinline__ uint32_t seg_claim(float v, float vmin, float scale, bool valid, uint32_t s_cnt, uint32_t s_wl, int &n_wl, uint32_t lt_mask)
 {
     const int bi = __float2int_rz((v - vmin) * scale);            // finite: >= 0; NaN -> 0
     uint32_t b = 1u + (uint32_t)min(bi, kSegNBF - 1);
@@ -549,11 +558,15 @@ __device__ __forceinline__ uint32_t seg_claim(float v, float vmin, float scale, 
     }
     const uint32_t w = b & (kSegNBHalf - 1), sh = (b >> 6) & 16u;
     uint32_t pk = 0u;
+    bool second = false;
     if (valid) {
         const uint32_t slot = (atoms_add(s_cnt + 4u * (w + (w >> 5)), 1u << sh) >> sh) & 0xffffu;
         pk = (b << 16) | slot;
-        if (slot == 1u && finite_bucket) sts_u16(s_wl + 2u * atoms_add(s_wlcount, 1u), b);
+        second = slot == 1u && finite_bucket;
     }
+    const uint32_t hit = __ballot_sync(0xffffffffu, second);
+    if (second) sts_u16(s_wl + 2u * (n_wl + __popc(hit & lt_mask)), b);
+    n_wl += __popc(hit);
     return pk;
 }
 
@@ -587,8 +600,11 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         const int cl = tid & (kSegWarps - 1);
         const float *src = temps + min(c0 + cl, C - 1);
         float *dst = (float *)(smem_raw + (size_t)cl * kSegWarpBytes + kSegOffSv);
-#pragma unroll 4
-        for (int k = tid / kSegWarps; k < NE; k += 32) dst[k] = src[(int64_t)st[k] * ld_t];
+        const uint32_t s_dst = smem_u32(dst);
+#pragma unroll 8
+        for (int k = tid / kSegWarps; k < NE; k += 32)            // asynchronous 4-byte copies: every load of the tile is in flight at once
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_dst + 4u * k), "l"(src + (int64_t)st[k] * ld_t) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();                                              // the only block-wide barrier
     const int64_t cell = c0 + warp;
@@ -597,7 +613,6 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     const uint32_t s_base = smem_u32(smem_raw + (size_t)warp * kSegWarpBytes);
     const uint32_t s_sv = s_base + kSegOffSv, s_cnt = s_base + kSegOffCnt, s_pb = s_cnt, s_rw = s_base + kSegOffRw,
                    s_wl = s_base + kSegOffWl, s_long = s_base + kSegOffLong, s_cum = s_rw;
-    const uint32_t s_wlcount = s_long + 124u;                     // last word of the long-run list area
 
     // ---- 1. samples into registers; min / max; non-finite census ----
     const float pinf = __int_as_float(0x7f800000);
@@ -616,7 +631,6 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         }
     }
     for (int i = lane; i < 1024 + 32; i += 32) sts_u32(s_cnt + 4u * i, 0u);
-    if (lane == 0) sts_u32(s_wlcount, 0u);
     int n_nan = 0, n_pinf = 0, n_ninf = 0;
     const bool nonfinite = __any_sync(0xffffffffu, odd);
     if (nonfinite) {                                              // rare: redo min / max over the finite samples only, count the rest
@@ -646,17 +660,19 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     const float range = vmax - vmin;
     const float scale = (range > 0.0f && range < pinf) ? (float)(kSegNBF - 1) / range : 0.0f;
     uint32_t pk[kSegRounds];                                      // bucket << 16 | slot
+    int n_wl = 0;                                                 // warp-uniform
+    const uint32_t lt_mask = (1u << lane) - 1u;
     if (!nonfinite) {
 #pragma unroll
         for (int m = 0; m < kSegRounds; m++) {
             pk[m] = 0u;
-            if (32 * m < NE) pk[m] = seg_claim<false>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, s_wlcount);
+            if (32 * m < NE) pk[m] = seg_claim<false>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, n_wl, lt_mask);
         }
     } else {
 #pragma unroll
         for (int m = 0; m < kSegRounds; m++) {
             pk[m] = 0u;
-            if (32 * m < NE) pk[m] = seg_claim<true>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, s_wlcount);
+            if (32 * m < NE) pk[m] = seg_claim<true>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, n_wl, lt_mask);
         }
     }
     __syncwarp();
@@ -692,7 +708,6 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     }
     __syncwarp();
     {
-        const int n_wl = (int)lds_u32(s_wlcount);
         int n_long = 0;
         for (int q0 = 0; q0 < n_wl; q0 += 32) {
             const int q = q0 + lane;
@@ -702,7 +717,14 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
                 const uint32_t b = lds_u16(s_wl + 2u * q);
                 const int i0 = seg_bucket_base(s_cnt, b), i1 = seg_bucket_base(s_cnt, b + 1u);
                 if (i1 - i0 > kSegLongRun) { is_long = true; desc = (uint32_t)i0 | ((uint32_t)i1 << 16); }
-                else {
+                else if (i1 - i0 == 2) {                          // the common case: one compare, maybe one swap
+                    const float v0 = lds_f32(s_sv + 4u * i0), v1 = lds_f32(s_sv + 4u * i0 + 4u);
+                    if (v0 > v1) {
+                        const uint32_t r0 = lds_u8(s_rw + i0), r1 = lds_u8(s_rw + i0 + 1);
+                        sts_f32(s_sv + 4u * i0, v1); sts_f32(s_sv + 4u * i0 + 4u, v0);
+                        sts_u8(s_rw + i0, r1); sts_u8(s_rw + i0 + 1, r0);
+                    }
+                } else {
                     for (int a = i0 + 1; a < i1; a++) {
                         const float ka = lds_f32(s_sv + 4u * a);
                         const uint32_t ra = lds_u8(s_rw + a);
@@ -785,8 +807,11 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     const int L_ninf = n_ninf, L_fin = NE - n_nan - n_pinf, L_pinf = NE - n_nan;   // where the finite / +inf / NaN samples begin
     const int d0 = sg * geo.S, nd = min(n_doy, d0 + geo.S) - d0;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int qi = lane; qi < nd * P; qi += 32) {
-        const int dl = qi / P, p = qi - dl * P, d = d0 + dl;
+    const int q_dl = 32 / P, q_p = 32 - q_dl * P;                // one round of 32 queries further: q_dl days and q_p percentiles
+    int dl = lane / P, p = lane - dl * P;
+    for (int qi = lane; qi < nd * P; qi += 32, dl += q_dl, p += q_p) {
+        if (p >= P) { p -= P; dl++; }
+        const int d = d0 + dl;
         const uint4 rg = doy_rng[d];
         const int n1 = (int)byte_of(rg, 0), n2 = (int)byte_of(rg, 1);
         const int pos_lo = s_sel.pos_lo[p], pos_hi = s_sel.pos_hi[p], mode = s_sel.mode[p];

@@ -464,16 +464,19 @@ __device__ __forceinline__ uint32_t byte_of(const uint4 &v, int i)
 
 // A window as row ranges over the segment's local rows: range k covers rows [lo_k, hi_k); ranges < n1 are the rows
 // pooled at least once, ranges n1 .. nr-1 the rows pooled twice.  ca/cb: shared addresses of cum rows hi/lo, pa/pb: of PB rows.
+// (Plain C++ loads here, not volatile PTX: nothing is written during the query phase, and the compiler is free to
+// interleave the independent dependency chains of the two queries a lane works on.)
 template <int NR>
 struct SegWin {
-    uint32_t ca[NR], cb[NR], pa[NR], pb[NR];
+    const uint16_t *ca[NR], *cb[NR];
+    const uint32_t *pa[NR], *pb[NR];
     int n1, nr;
     __device__ __forceinline__ int before(int w) const            // members in words < w
     {
         int cnt = 0;
 #pragma unroll
         for (int k = 0; k < NR; k++)
-            if (NR == 1 || k < nr) cnt += (int)lds_u16(ca[k] + 2u * w) - (int)lds_u16(cb[k] + 2u * w);
+            if (NR == 1 || k < nr) cnt += (int)ca[k][w] - (int)cb[k][w];
         return cnt;
     }
     __device__ __forceinline__ void bits(int w, uint32_t &a, uint32_t &b) const   // a: members of word w, b: members pooled twice
@@ -482,7 +485,7 @@ struct SegWin {
 #pragma unroll
         for (int k = 0; k < NR; k++)
             if (NR == 1 || k < nr) {
-                const uint32_t v = lds_u32(pa[k] + 4u * w) ^ lds_u32(pb[k] + 4u * w);
+                const uint32_t v = pa[k][w] ^ pb[k][w];
                 if (NR == 1 || k < n1) a |= v; else b |= v;
             }
     }
@@ -523,6 +526,43 @@ __device__ __forceinline__ void seg_pick(const SegWin<NR> &win, int pos_lo, int 
     }
 }
 
+// The same for TWO single-range windows at once: two independent dependency chains in straight-line code.
+__device__ __forceinline__ void seg_pick2(const SegWin<1> &wa, const SegWin<1> &wb, int lo_a, int hi_a, int lo_b, int hi_b,
+                                          int &lr_lo_a, int &lr_hi_a, int &lr_lo_b, int &lr_hi_b)
+{
+    int w_a = 0, bw_a = 0, w_b = 0, bw_b = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int c_a = wa.before(w_a + step), c_b = wb.before(w_b + step);
+        if (c_a <= lo_a) { w_a += step; bw_a = c_a; }
+        if (c_b <= lo_b) { w_b += step; bw_b = c_b; }
+    }
+    uint32_t a_a, a_b, unused;
+    wa.bits(w_a, a_a, unused);
+    wb.bits(w_b, a_b, unused);
+    int n_a = lo_a - bw_a, n_b = lo_b - bw_b, bit_a = 0, bit_b = 0;
+    uint32_t t_a = a_a, t_b = a_b;
+#pragma unroll
+    for (int width = 16; width >= 1; width >>= 1) {
+        const uint32_t mask = (1u << width) - 1u;
+        const int c_a = __popc(t_a & mask), c_b = __popc(t_b & mask);
+        if (n_a >= c_a) { n_a -= c_a; bit_a += width; t_a >>= width; }
+        if (n_b >= c_b) { n_b -= c_b; bit_b += width; t_b >>= width; }
+    }
+    lr_lo_a = w_a * 32 + bit_a; lr_hi_a = lr_lo_a;
+    lr_lo_b = w_b * 32 + bit_b; lr_hi_b = lr_lo_b;
+    if (hi_a != lo_a) {                                           // hi == lo + 1 here: the next set bit, in this word or a later one
+        a_a &= 0xfffffffeu << bit_a;
+        while (a_a == 0u && w_a < 31) { w_a++; wa.bits(w_a, a_a, unused); }
+        lr_hi_a = w_a * 32 + __ffs(a_a) - 1;
+    }
+    if (hi_b != lo_b) {
+        a_b &= 0xfffffffeu << bit_b;
+        while (a_b == 0u && w_b < 31) { w_b++; wb.bits(w_b, a_b, unused); }
+        lr_hi_b = w_b * 32 + __ffs(a_b) - 1;
+    }
+}
+
 // members of the window at sorted positions < L
 template <int NR>
 __device__ __forceinline__ int seg_below(const SegWin<NR> &win, int L, int n)
@@ -541,33 +581,45 @@ __device__ __forceinline__ int seg_bucket_base(uint32_t s_cnt, uint32_t b)
     return (int)((lds_u32(s_cnt + 4u * (w + (w >> 5))) >> ((b >> 6) & 16u)) & 0xffffu);
 }
 
-// phase 2 for one register round: bucket, slot; the lanes that draw slot 1 append their bucket to the work list
+// phase 2 for a batch of kSegBatch register rounds: buckets first, then all the atomics of the batch back to back (their
+// latencies overlap), then slots; the lanes that draw slot 1 append their bucket to the work list.
+// pk = counter byte offset << 9 (word aligned: bits 11..) | half << 10 | slot.
+constexpr int kSegBatch = 8;
 template <bool kNonFinite>
-__device__ __forceinline__ uint32_t seg_claim(float v, float vmin, float scale, bool valid, uint32_t s_cnt, uint32_t s_wl, int &n_wl, uint32_t lt_mask)
+__device__ __forceinline__ void seg_claim(const float *x, uint32_t *pk, int m0, int nl /* NE - lane */, float vmin, float scale,
+                                          uint32_t s_cnt, uint32_t s_wl, int &n_wl, uint32_t lt_mask)
 {
-    const int bi = __float2int_rz((v - vmin) * scale);            // finite: >= 0; NaN -> 0
-    uint32_t b = 1u + (uint32_t)min(bi, kSegNBF - 1);
-    bool finite_bucket = true;
-    if (kNonFinite) {
-        const float pinf = __int_as_float(0x7f800000);
-        b = 1u + (uint32_t)min(max(bi, 0), kSegNBF - 1);
-        if (v == pinf) b = (uint32_t)kSegNB - 3u;
-        if (v == -pinf) b = 0u;
-        if (v != v) b = (uint32_t)kSegNB - 2u;
-        finite_bucket = b - 1u < (uint32_t)kSegNBF;
+    uint32_t bb[kSegBatch], old[kSegBatch];
+#pragma unroll
+    for (int j = 0; j < kSegBatch; j++) {
+        const float v = x[m0 + j];
+        const int bi = __float2int_rz((v - vmin) * scale);        // finite: >= 0; NaN -> 0
+        uint32_t b = 1u + (uint32_t)min(bi, kSegNBF - 1);
+        if (kNonFinite) {
+            const float pinf = __int_as_float(0x7f800000);
+            b = 1u + (uint32_t)min(max(bi, 0), kSegNBF - 1);
+            if (v == pinf) b = (uint32_t)kSegNB - 3u;
+            if (v == -pinf) b = 0u;
+            if (v != v) b = (uint32_t)kSegNB - 2u;
+        }
+        bb[j] = b;
     }
-    const uint32_t w = b & (kSegNBHalf - 1), sh = (b >> 6) & 16u;
-    uint32_t pk = 0u;
-    bool second = false;
-    if (valid) {
-        const uint32_t slot = (atoms_add(s_cnt + 4u * (w + (w >> 5)), 1u << sh) >> sh) & 0xffffu;
-        pk = (b << 16) | slot;
-        second = slot == 1u && finite_bucket;
+#pragma unroll
+    for (int j = 0; j < kSegBatch; j++) {
+        const uint32_t w = bb[j] & (kSegNBHalf - 1), sh = (bb[j] >> 6) & 16u;
+        old[j] = 0u;
+        if (nl > 32 * (m0 + j)) old[j] = atoms_add(s_cnt + 4u * (w + (w >> 5)), 1u << sh);
     }
-    const uint32_t hit = __ballot_sync(0xffffffffu, second);
-    if (second) sts_u16(s_wl + 2u * (n_wl + __popc(hit & lt_mask)), b);
-    n_wl += __popc(hit);
-    return pk;
+#pragma unroll
+    for (int j = 0; j < kSegBatch; j++) {
+        const uint32_t b = bb[j], w = b & (kSegNBHalf - 1), half = (b >> 10) & 1u;   // (masked: lanes without a sample hold garbage)
+        const uint32_t slot = (old[j] >> (half << 4)) & 0xffffu;
+        pk[m0 + j] = ((w + (w >> 5)) << 11) | (half << 10) | slot;
+        const bool second = nl > 32 * (m0 + j) && slot == 1u && (!kNonFinite || b - 1u < (uint32_t)kSegNBF);
+        const uint32_t hit = __ballot_sync(0xffffffffu, second);
+        if (second) sts_u16(s_wl + 2u * (n_wl + __popc(hit & lt_mask)), b);
+        n_wl += __popc(hit);
+    }
 }
 
 __global__ void __launch_bounds__(kSegWarps * 32, 2)
@@ -620,14 +672,19 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     float vmin = pinf, vmax = -pinf;
     bool odd = false;                                             // some valid sample is NaN or +-inf
 #pragma unroll
-    for (int m = 0; m < kSegRounds; m++) {
-        x[m] = 0.0f;
-        if (32 * m < NE) {                                        // warp-uniform
-            const float v = lds_f32(s_sv + 4u * (32 * m + lane));
-            x[m] = v;
-            const bool valid = lane < NE - 32 * m;
-            odd |= valid && !(fabsf(v) < pinf);
-            if (valid) { vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
+    for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
+#pragma unroll
+        for (int j = 0; j < kSegBatch; j++) x[m0 + j] = 0.0f;
+        if (32 * m0 < NE) {                                       // warp-uniform
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) x[m0 + j] = lds_f32(s_sv + 4u * (32 * (m0 + j) + lane));
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) {
+                const float v = x[m0 + j];
+                const bool valid = NE - lane > 32 * (m0 + j);
+                odd |= valid && !(fabsf(v) < pinf);
+                if (valid) { vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
+            }
         }
     }
     for (int i = lane; i < 1024 + 32; i += 32) sts_u32(s_cnt + 4u * i, 0u);
@@ -659,20 +716,23 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     // ---- 2. monotone buckets; one atomic claims the slot inside the bucket ----
     const float range = vmax - vmin;
     const float scale = (range > 0.0f && range < pinf) ? (float)(kSegNBF - 1) / range : 0.0f;
-    uint32_t pk[kSegRounds];                                      // bucket << 16 | slot
+    uint32_t pk[kSegRounds];                                      // where the counter is | slot
     int n_wl = 0;                                                 // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int nl = NE - lane;                                     // round m holds a sample of this lane iff nl > 32 m
     if (!nonfinite) {
 #pragma unroll
-        for (int m = 0; m < kSegRounds; m++) {
-            pk[m] = 0u;
-            if (32 * m < NE) pk[m] = seg_claim<false>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, n_wl, lt_mask);
+        for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
+            if (32 * m0 < NE) seg_claim<false>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
         }
     } else {
 #pragma unroll
-        for (int m = 0; m < kSegRounds; m++) {
-            pk[m] = 0u;
-            if (32 * m < NE) pk[m] = seg_claim<true>(x[m], vmin, scale, lane < NE - 32 * m, s_cnt, s_wl, n_wl, lt_mask);
+        for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
+            if (32 * m0 < NE) seg_claim<true>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
         }
     }
     __syncwarp();
@@ -699,11 +759,19 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
 
     // ---- 4. scatter (value, local row) to the sorted position; exact order inside the work-list buckets ----
 #pragma unroll
-    for (int m = 0; m < kSegRounds; m++) {
-        if (32 * m < NE && lane < NE - 32 * m) {
-            const int pos = seg_bucket_base(s_cnt, pk[m] >> 16) + (int)(pk[m] & 0xffffu);
-            sts_f32(s_sv + 4u * pos, x[m]);
-            sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
+    for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
+        if (32 * m0 < NE) {                                       // warp-uniform
+            uint32_t bw[kSegBatch];
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) bw[j] = lds_u32(s_cnt + ((pk[m0 + j] >> 9) & ~3u));   // the batch's base lookups overlap
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) {
+                if (nl > 32 * (m0 + j)) {
+                    const uint32_t pos = ((bw[j] >> ((pk[m0 + j] >> 6) & 16u)) & 0xffffu) + (pk[m0 + j] & 1023u);
+                    sts_f32(s_sv + 4u * pos, x[m0 + j]);
+                    sts_u8(s_rw + pos, ((uint32_t)(32 * (m0 + j) + lane) * (uint32_t)geo.ny_magic) >> 16);
+                }
+            }
         }
     }
     __syncwarp();
@@ -779,9 +847,16 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     for (int i = lane; i < kSegRowsMax * kSegPst; i += 32) sts_u32(s_pb + 4u * i, 0u);
     __syncwarp();
 #pragma unroll
-    for (int m = 0; m < kSegRounds; m++)
-        if (32 * m < NE && lane < NE - 32 * m)
-            reds_or(s_pb + 4u * (lds_u8(s_rw + 32 * m + lane) * kSegPst + m), 1u << lane);
+    for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
+        if (32 * m0 < NE) {                                       // warp-uniform
+            uint32_t rr[kSegBatch];
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) rr[j] = lds_u8(s_rw + 32 * (m0 + j) + lane);
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++)
+                if (nl > 32 * (m0 + j)) reds_or(s_pb + 4u * (rr[j] * kSegPst + (m0 + j)), 1u << lane);
+        }
+    }
     __syncwarp();
     {
         uint32_t acc = 0u;
@@ -803,14 +878,16 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     }
     __syncwarp();
 
-    // ---- 6. queries: one (day of the segment, percentile) per lane ----
+    // ---- 6. queries: one (day of the segment, percentile) per lane, two rounds of 32 queries in flight ----
     const int L_ninf = n_ninf, L_fin = NE - n_nan - n_pinf, L_pinf = NE - n_nan;   // where the finite / +inf / NaN samples begin
     const int d0 = sg * geo.S, nd = min(n_doy, d0 + geo.S) - d0;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const int q_dl = 32 / P, q_p = 32 - q_dl * P;                // one round of 32 queries further: q_dl days and q_p percentiles
-    int dl = lane / P, p = lane - dl * P;
-    for (int qi = lane; qi < nd * P; qi += 32, dl += q_dl, p += q_p) {
-        if (p >= P) { p -= P; dl++; }
+    const unsigned char *wbase = smem_raw + (size_t)warp * kSegWarpBytes;
+    const float *sv_p = (const float *)(wbase + kSegOffSv);
+    const uint32_t *pb_p = (const uint32_t *)(wbase + kSegOffCnt);
+    const uint16_t *cum_p = (const uint16_t *)(wbase + kSegOffRw);
+    double *out_c = out + cell * n_doy * (int64_t)P;
+
+    auto answer = [&](int dl, int p) {
         const int d = d0 + dl;
         const uint4 rg = doy_rng[d];
         const int n1 = (int)byte_of(rg, 0), n2 = (int)byte_of(rg, 1);
@@ -819,8 +896,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         if (n1 == 1 && n2 == 0) {                                 // one contiguous run of rows, each pooled once (almost every day)
             SegWin<1> win;
             const uint32_t r0 = byte_of(rg, 2), r1 = byte_of(rg, 5);
-            win.ca[0] = s_cum + 2u * (r1 * kSegCst); win.cb[0] = s_cum + 2u * (r0 * kSegCst);
-            win.pa[0] = s_pb + 4u * (r1 * kSegPst); win.pb[0] = s_pb + 4u * (r0 * kSegPst);
+            win.ca[0] = cum_p + r1 * kSegCst; win.cb[0] = cum_p + r0 * kSegCst;
+            win.pa[0] = pb_p + r1 * kSegPst; win.pb[0] = pb_p + r0 * kSegPst;
             win.n1 = 1; win.nr = 1;
             seg_pick<1>(win, pos_lo, pos_hi, lr_lo, lr_hi);
             if (nonfinite) {
@@ -840,8 +917,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
                 for (int j = 0; j < 3; j++) if (k == j && j < n1) { r0 = byte_of(rg, 2 + j); r1 = byte_of(rg, 5 + j); }
 #pragma unroll
                 for (int j = 0; j < 2; j++) if (k == n1 + j && j < n2) { r0 = byte_of(rg, 8 + j); r1 = byte_of(rg, 10 + j); }
-                win.ca[k] = s_cum + 2u * (r1 * kSegCst); win.cb[k] = s_cum + 2u * (r0 * kSegCst);
-                win.pa[k] = s_pb + 4u * (r1 * kSegPst); win.pb[k] = s_pb + 4u * (r0 * kSegPst);
+                win.ca[k] = cum_p + r1 * kSegCst; win.cb[k] = cum_p + r0 * kSegCst;
+                win.pa[k] = pb_p + r1 * kSegPst; win.pb[k] = pb_p + r0 * kSegPst;
             }
             seg_pick<kSegRanges>(win, pos_lo, pos_hi, lr_lo, lr_hi);
             if (nonfinite) {
@@ -851,7 +928,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
                 w_nan = n - b_pinf;
             }
         }
-        const double lower = (double)lds_f32(s_sv + 4u * lr_lo), upper = (double)lds_f32(s_sv + 4u * lr_hi);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        const double lower = (double)sv_p[lr_lo], upper = (double)sv_p[lr_hi];
         double v;
         if (mode == kSelInterp) {                                 // arraymath.py:1697-1701
             v = __dadd_rn(__dmul_rn(lower, s_sel.w_lo[p]), __dmul_rn(upper, s_sel.w_hi[p]));
@@ -869,7 +947,41 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
             }
         }
         if (w_nan > 0) v = nan;                                   // _can_collect_percentiles, arraymath.py:1714
-        out[(cell * n_doy + d) * (int64_t)P + p] = v;
+        out_c[d * P + p] = v;
+    };
+
+    // both queries of a lane on the common path (one run of rows, plain interpolation, finite samples): worked on together
+    auto answer2 = [&](int dl_a, int p_a, int dl_b, int p_b) -> bool {
+        const uint4 rg_a = doy_rng[d0 + dl_a], rg_b = doy_rng[d0 + dl_b];
+        const int lo_a = s_sel.pos_lo[p_a], hi_a = s_sel.pos_hi[p_a], lo_b = s_sel.pos_lo[p_b], hi_b = s_sel.pos_hi[p_b];
+        const bool plain = (rg_a.x & 0xffffu) == 1u && (rg_b.x & 0xffffu) == 1u && s_sel.mode[p_a] == kSelInterp && s_sel.mode[p_b] == kSelInterp &&
+                           hi_a - lo_a <= 1 && hi_b - lo_b <= 1;
+        if (!plain) return false;
+        SegWin<1> wa, wb;
+        const uint32_t r0a = byte_of(rg_a, 2), r1a = byte_of(rg_a, 5), r0b = byte_of(rg_b, 2), r1b = byte_of(rg_b, 5);
+        wa.ca[0] = cum_p + r1a * kSegCst; wa.cb[0] = cum_p + r0a * kSegCst; wa.pa[0] = pb_p + r1a * kSegPst; wa.pb[0] = pb_p + r0a * kSegPst;
+        wb.ca[0] = cum_p + r1b * kSegCst; wb.cb[0] = cum_p + r0b * kSegCst; wb.pa[0] = pb_p + r1b * kSegPst; wb.pb[0] = pb_p + r0b * kSegPst;
+        wa.n1 = wa.nr = wb.n1 = wb.nr = 1;
+        int la, ha, lb, hb;
+        seg_pick2(wa, wb, lo_a, hi_a, lo_b, hi_b, la, ha, lb, hb);
+        out_c[(d0 + dl_a) * P + p_a] = __dadd_rn(__dmul_rn((double)sv_p[la], s_sel.w_lo[p_a]), __dmul_rn((double)sv_p[ha], s_sel.w_hi[p_a]));
+        out_c[(d0 + dl_b) * P + p_b] = __dadd_rn(__dmul_rn((double)sv_p[lb], s_sel.w_lo[p_b]), __dmul_rn((double)sv_p[hb], s_sel.w_hi[p_b]));
+        return true;
+    };
+
+    const int q_dl = 32 / P, q_p = 32 - q_dl * P;                // one round of 32 queries further: q_dl days and q_p percentiles
+    int dl = lane / P, p = lane - dl * P;
+    const int nq = nd * P;
+    for (int qi = lane; qi < nq; qi += 64) {
+        int dl2 = dl + q_dl, p2 = p + q_p;
+        if (p2 >= P) { p2 -= P; dl2++; }
+        const bool two = qi + 32 < nq;
+        if (!(two && !nonfinite && answer2(dl, p, dl2, p2))) {
+            answer(dl, p);
+            if (two) answer(dl2, p2);
+        }
+        dl = dl2 + q_dl; p = p2 + q_p;
+        if (p >= P) { p -= P; dl++; }
     }
 }
 

@@ -110,14 +110,16 @@ k_unpack_mask(const uint32_t *__restrict__ hot, int64_t C, int64_t T, int P, int
 // ----------------------------------------------------------------------------------------------------
 // One thread per (cell, percentile); lanes = 32 neighbouring cells.  Every definition's state machine
 // (reference index_heatwaves, hdp/metric.py:39-58) is advanced BIT-PARALLEL: bit i of each state word
-// belongs to definition i, so one hot run costs the same ~25 logic instructions for 1 or 32 definitions.
+// belongs to definition i, so one hot run costs the same logic instructions for 1 or 32 definitions.
 //   inhw        bit i = in_heatwave of definition i
 //   rem[k]      bit-sliced down counter: remaining subsequent events = max_subs - sub_events
 //   fresh       bit i = the next labelled run of definition i starts a heatwave id not yet seen in the open season
-// Lanes pop their own events (each lane advances through its hot words at its own pace), so the warp
-// stays converged on the event body instead of idling behind the busiest cell.
-// Season accumulators are packed two definitions per register (16-bit halves): cnt (days of the current
-// id in the open season), HWF, HWN, HWD.
+// The loop is FLAT and lane-asynchronous: in one step a lane pops one hot run of its current word (if it has one) and
+// then, if the word is used up, moves on to its next word.  Both halves are predicated, so the warp stays converged on
+// one short body whatever the lanes' run patterns are; a lane needs max(1, runs) steps per word.
+// Season accumulators are packed SIMD-in-register: four definitions per register (8-bit lanes) when no season is longer
+// than 255 days, else two (16-bit lanes): cnt (days of the current id in the open season), HWF, HWN, HWD.  Seasons are
+// closed with the whole warp converged on the stores.
 //
 // Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
 // (the host splits overlapping tables into several passes, one launch each).
@@ -126,35 +128,36 @@ struct ScanTables {
     int ge_len, brk_len;             // table lengths: max(min_dur) + 2, max(max_break) + 2
 };
 
-template <int NP, int KS>
-__global__ void __launch_bounds__(256)
+constexpr int kScanWarps = 8;
+
+// NG accumulator registers per metric; kBytes: 4 definitions per register (8-bit lanes), else 2 (16-bit lanes)
+template <int NG, int KS, bool kBytes>
+__global__ void __launch_bounds__(kScanWarps * 32, NG <= 4 && KS <= 2 ? 4 : 2)
 k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
        int P, int D, const __grid_constant__ ScanTables tabs, const uint32_t *__restrict__ ge_tab, const uint32_t *__restrict__ brk_tab,
        const int4 *__restrict__ seasons_north, int n_north, const int4 *__restrict__ seasons_south, int n_south, int Y,
        const uint8_t *__restrict__ is_south, uint16_t *__restrict__ out)
 {
+    constexpr int PER = kBytes ? 4 : 2, BITS = kBytes ? 8 : 16;
+    constexpr uint32_t LANE_MASK = kBytes ? 0xffu : 0xffffu;
     extern __shared__ uint32_t smem_scan[];
-    uint4 *lut8 = (uint4 *)smem_scan;                             // [256]: byte of definition bits -> 4 pair selectors
-    uint32_t *ge_s = smem_scan + 256 * 4;                         // [ge_len]  definitions with min_dur <= len
+    uint32_t *ge_s = smem_scan;                                   // [ge_len]  definitions with min_dur <= len
     uint32_t *brk_s = ge_s + tabs.ge_len;                         // [brk_len] definitions with max_break < gap
-    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 1] first day of every hot word (last = T)
-    const int tid = threadIdx.y * 32 + threadIdx.x, nthreads = blockDim.y * 32;
-    for (int b = tid; b < 256; b += nthreads) {
-        uint4 v;
-        v.x = (b & 1) | ((b >> 1 & 1) << 16);
-        v.y = (b >> 2 & 1) | ((b >> 3 & 1) << 16);
-        v.z = (b >> 4 & 1) | ((b >> 5 & 1) << 16);
-        v.w = (b >> 6 & 1) | ((b >> 7 & 1) << 16);
-        lut8[b] = v;
-    }
+    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 2] first day of every hot word; word K is a virtual cold day at T
+    const int tid = threadIdx.x, nthreads = kScanWarps * 32;
     for (int i = tid; i < tabs.ge_len; i += nthreads) ge_s[i] = ge_tab[i];
     for (int i = tid; i < tabs.brk_len; i += nthreads) brk_s[i] = brk_tab[i];
-    for (int i = tid; i <= K; i += nthreads) word_t0[i] = i < K ? words[i].x : T;
+    for (int i = tid; i <= K + 1; i += nthreads) word_t0[i] = i < K ? words[i].x : T + (i - K);
     __syncthreads();
 
-    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    const int p = blockIdx.y * blockDim.y + threadIdx.y;
-    if (c >= C || p >= P) return;
+    // warp -> (group of 32 cells, percentile): every warp of the grid has work
+    const int lane = tid & 31;
+    const int64_t wg = (int64_t)blockIdx.x * kScanWarps + (tid >> 5);
+    const int64_t cg = wg / P;
+    const int p = (int)(wg - cg * P);
+    if (cg * 32 >= C) return;                                     // warp-uniform
+    const bool alive = cg * 32 + lane < C;                        // lanes past the last cell shadow it (the warp votes with all 32 lanes)
+    const int64_t c = alive ? cg * 32 + lane : C - 1;
 
     const bool south = is_south != nullptr && is_south[c] != 0;
     const int4 *seas = south ? seasons_south : seasons_north;
@@ -167,27 +170,27 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     uint32_t rem[KS];
 #pragma unroll
     for (int k = 0; k < KS; k++) { rem[k] = tabs.max_subs_plane[k]; sublt |= rem[k]; }     // sub_events = 0
-    uint32_t cnt2[NP], hwf2[NP], hwn2[NP], hwd2[NP];              // definitions 2j (low half) and 2j+1 (high half)
+    uint32_t cntg[NG], hwfg[NG], hwng[NG], hwdg[NG];              // definitions PER * j .. PER * j + PER - 1
 #pragma unroll
-    for (int j = 0; j < NP; j++) { cnt2[j] = 0u; hwf2[j] = 0u; hwn2[j] = 0u; hwd2[j] = 0u; }
+    for (int j = 0; j < NG; j++) { cntg[j] = 0u; hwfg[j] = 0u; hwng[j] = 0u; hwdg[j] = 0u; }
 
     const int64_t plane = (int64_t)P * D * Y * C;                 // one metric
     auto flush = [&]() {                                          // close season `ys`
 #pragma unroll
-        for (int j = 0; j < NP; j++) {
+        for (int j = 0; j < NG; j++) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int d = 2 * j + h;
-                if (d < D) {
-                    const uint32_t f = (hwf2[j] >> (16 * h)) & 0xffffu, nn = (hwn2[j] >> (16 * h)) & 0xffffu;
+            for (int h = 0; h < PER; h++) {
+                const int d = PER * j + h;
+                if (d < D && alive) {
+                    const uint32_t f = (hwfg[j] >> (BITS * h)) & LANE_MASK, nn = (hwng[j] >> (BITS * h)) & LANE_MASK;
                     const int64_t o = (((int64_t)p * D + d) * Y + row_cur) * C + c;
                     out[o] = (uint16_t)f;
                     out[o + plane] = (uint16_t)nn;
-                    out[o + 2 * plane] = (uint16_t)(hwd2[j] >> (16 * h));
+                    out[o + 2 * plane] = (uint16_t)((hwdg[j] >> (BITS * h)) & LANE_MASK);
                     out[o + 3 * plane] = (uint16_t)(nn ? f / nn : 0u);       // trunc(mean), metric.py:340
                 }
             }
-            cnt2[j] = 0u; hwf2[j] = 0u; hwn2[j] = 0u; hwd2[j] = 0u;
+            cntg[j] = 0u; hwfg[j] = 0u; hwng[j] = 0u; hwdg[j] = 0u;
         }
         fresh = 0xffffffffu;
         ys++;
@@ -195,101 +198,104 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
         else { a_cur = INT_MAX; b_cur = INT_MAX; }
     };
 
-    int prev_e = -(1 << 29);      // end of the previous hot run
-    int run_start = -1;           // start of the hot run still open at the end of the previous word
-    const uint32_t *hp = hot + (int64_t)p * K * C + c;
-    const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
-
+    // definition bits -> one 0/1 per accumulator lane
+    auto spread = [](uint32_t bits, int j) -> uint32_t {
+        if (kBytes) return (((bits >> (4 * j)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        const uint32_t t = bits >> (2 * j);
+        return (t & 1u) | ((t & 2u) << 15);
+    };
     // accounting of `days` heatwave days of the definitions in `lab` to the open season (HWF/HWN/HWD, metric.py:63-137)
     auto account = [&](uint32_t lab, uint32_t days) {
         const uint32_t newly = lab & fresh;                       // first labelled run of an id inside this season
         fresh &= ~lab;
 #pragma unroll
-        for (int j0 = 0; j0 < NP; j0 += 4) {
-            const uint4 sl = lut8[(lab >> (2 * j0)) & 255u], sn = lut8[(newly >> (2 * j0)) & 255u];
-            const uint32_t sel[4] = {sl.x, sl.y, sl.z, sl.w}, neu[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (j0 + q < NP) {
-                    const int j = j0 + q;
-                    cnt2[j] = (cnt2[j] & ~(neu[q] * 0xffffu)) + days * sel[q];
-                    hwf2[j] += days * sel[q];
-                    hwn2[j] += neu[q];
-                    hwd2[j] = __vmaxu2(hwd2[j], cnt2[j]);
-                }
-            }
+        for (int j = 0; j < NG; j++) {
+            const uint32_t sel = spread(lab, j), neu = spread(newly, j), add = days * sel;
+            cntg[j] = (cntg[j] & ~(neu * LANE_MASK)) + add;
+            hwfg[j] += add;
+            hwng[j] += neu;
+            hwdg[j] = kBytes ? __vmaxu4(hwdg[j], cntg[j]) : __vmaxu2(hwdg[j], cntg[j]);
         }
     };
 
+    int prev_e = -(1 << 29);      // end of the previous hot run
+    int run_start = -1;           // start of the hot run still open at the end of the previous word
+    const uint32_t *hp = hot + (int64_t)p * K * C + c;
+    const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
+
     int k = -1, t0 = 0;
     uint32_t starts = 0u, ends = 0u;
-    uint32_t m_next = K > 0 ? hp[0] : 0u;
+    uint32_t m_next = K > 0 ? hp[0] : 0u, m_next2 = K > 1 ? hp[C] : 0u;     // the hot words two steps ahead are in flight
+    const uint32_t *hp_ahead = hp + 2 * C;                        // word k + 3 while the lane is at word k
     uint32_t pend_lab = 0u;       // labelled run that continues past the end of the season being closed
     int pend_s = 0, pend_e = 0;
 
     // One iteration per season of this lane's table: consume (lane-asynchronously) every run that starts
     // before the season ends, then close the season with the whole warp converged on the stores.
-    for (; ys < n_seasons;) {
-        if (pend_lab) {
+    const int n_iter = max(n_north, n_south);                     // warp-uniform trip count; a lane whose table is shorter idles
+    for (int it = 0; it < n_iter; it++) {
+        const bool open = ys < n_seasons;
+        bool done = !open;                                        // this lane has nothing more to do before the season closes
+        if (open && pend_lab) {
             const int days = min(pend_e, b_cur) - max(pend_s, a_cur);
             if (days > 0) account(pend_lab, (uint32_t)days);
-            if (pend_e <= b_cur) pend_lab = 0u;
+            if (pend_e <= b_cur) pend_lab = 0u; else done = true;
         }
-        while (pend_lab == 0u) {
-            // ---- refill: advance through hot words until this lane has a run end to process ----
-            while (ends == 0u) {
+        while (__any_sync(0xffffffffu, !done)) {
+            if (!done && ends != 0u) {
+                // ---- the next hot run [s, e) of the current word: leave it queued if it starts after this season ----
+                const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
+                if (s >= b_cur) done = true;
+                else {
+                    const int e = t0 + __ffs(ends) - 1;
+                    ends &= ends - 1;
+                    if (run_start >= 0) run_start = -1; else starts &= starts - 1;
+                    const int len = e - s, gap = s - prev_e;
+                    prev_e = e;
+
+                    // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
+                    const uint32_t ge = ge_s[min(len, ge_cap)];   // len >= min_duration
+                    inhw &= ~brk_s[min(gap, brk_cap)];            // B: the break before this run was too long
+                    const uint32_t A = ~inhw & ge;                // A: a new heatwave starts
+                    const uint32_t Cm = inhw & sublt;             // C: subsequent event of the current heatwave
+                    const uint32_t Dm = inhw & ~sublt;            // D: subsequent events used up
+                    const uint32_t Dn = Dm & ge;                  //    ... long enough: new heatwave id
+                    const uint32_t lab = A | Cm | Dn;
+                    fresh |= A | Dn;
+                    inhw = (inhw | A) & ~(Dm & ~ge);
+                    uint32_t borrow = Cm;
+                    sublt = 0u;
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {                // rem -= 1 where C, rem = max_subs where D
+                        const uint32_t t = ~rem[q] & borrow;
+                        rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
+                        borrow = t;
+                        sublt |= rem[q];
+                    }
+                    const int days = min(e, b_cur) - max(s, a_cur);
+                    if (lab != 0u && days > 0) account(lab, (uint32_t)days);
+                    if (lab != 0u && e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; done = true; }
+                }
+            }
+            if (!done && ends == 0u) {
+                // ---- the word is used up: on to the next one ----
                 if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }   // at most one start is left: the run stays open
                 k++;
-                if (k > K) break;
-                uint32_t m = 0u;
-                int nb = 1;
-                t0 = T;                                           // word K is a virtual cold day closing a run at the series end
-                if (k < K) {
+                if (k > K) done = true;                           // series exhausted
+                else {
                     t0 = word_t0[k];
-                    nb = word_t0[k + 1] - t0;
-                    m = m_next;
-                    m_next = (k + 1 < K) ? hp[(int64_t)(k + 1) * C] : 0u;
+                    const int nb = word_t0[k + 1] - t0;           // (1 for the virtual word K: a cold day closing a run at the series end)
+                    const uint32_t m = k < K ? m_next : 0u;
+                    m_next = m_next2;
+                    if (k + 2 < K) m_next2 = *hp_ahead;
+                    hp_ahead += C;
+                    const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);   // bit i = day i-1 hot
+                    starts = m & ~prev;
+                    ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
                 }
-                const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);   // bit i = day i-1 hot
-                starts = m & ~prev;
-                ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-            }
-            if (ends == 0u) break;                                // series exhausted
-            // ---- next hot run [s, e): leave it queued if it starts after this season ----
-            const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
-            if (s >= b_cur) break;
-            const int e = t0 + __ffs(ends) - 1;
-            ends &= ends - 1;
-            if (run_start >= 0) run_start = -1; else starts &= starts - 1;
-            const int len = e - s, gap = s - prev_e;
-            prev_e = e;
-
-            // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
-            const uint32_t ge = ge_s[min(len, ge_cap)];           // len >= min_duration
-            inhw &= ~brk_s[min(gap, brk_cap)];                    // B: the break before this run was too long
-            const uint32_t A = ~inhw & ge;                        // A: a new heatwave starts
-            const uint32_t Cm = inhw & sublt;                     // C: subsequent event of the current heatwave
-            const uint32_t Dm = inhw & ~sublt;                    // D: subsequent events used up
-            const uint32_t Dn = Dm & ge;                          //    ... long enough: new heatwave id
-            const uint32_t lab = A | Cm | Dn;
-            fresh |= A | Dn;
-            inhw = (inhw | A) & ~(Dm & ~ge);
-            uint32_t borrow = Cm;
-            sublt = 0u;
-#pragma unroll
-            for (int q = 0; q < KS; q++) {                        // rem -= 1 where C, rem = max_subs where D
-                const uint32_t t = ~rem[q] & borrow;
-                rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
-                borrow = t;
-                sublt |= rem[q];
-            }
-            if (lab) {
-                const int days = min(e, b_cur) - max(s, a_cur);
-                if (days > 0) account(lab, (uint32_t)days);
-                if (e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; }
             }
         }
-        flush();
+        if (open) flush();
     }
 }
 
@@ -557,12 +563,19 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         for (int i = 0; i < D; i++) if (h_defs[3 * i + 1] < g) lut[tabs.ge_len + g] |= 1u << i;
     HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
     const uint32_t *ge_tab = L.lut, *brk_tab = L.lut + tabs.ge_len;
-    const size_t scan_smem = (256 * 4 + lut.size() + (size_t)K + 1) * sizeof(uint32_t);
+    const size_t scan_smem = (lut.size() + (size_t)K + 2) * sizeof(uint32_t);
     if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~45 000 hot words (~4 000 years of daily data)
-    const int pw = std::min(P, 8);
-    dim3 block(32, pw);
-    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((P + pw - 1) / pw));
-    const int np = D <= 6 ? 3 : D <= 8 ? 4 : D <= 16 ? 8 : D <= 24 ? 12 : 16;
+    const int64_t n_warps = ((C + 31) / 32) * P;                             // one warp per (32 cells, percentile)
+    const unsigned scan_grid = (unsigned)((n_warps + kScanWarps - 1) / kScanWarps);
+    // accumulators: four definitions per register when every season fits 8-bit lanes, else two
+    int max_season = 0;
+    for (int h = 0; h < 2; h++)
+        for (const auto &pass : passes[h])
+            for (const Season &se : pass) max_season = std::max(max_season, se.b - se.a);
+    const bool bytes = max_season <= 255;
+    const int per = bytes ? 4 : 2;
+    int ng = (D + per - 1) / per;
+    ng = ng <= 2 ? 2 : ng <= 3 ? 3 : ng <= 4 ? 4 : ng <= 6 ? 6 : ng <= 8 ? 8 : ng <= 12 ? 12 : 16;
     const int ks = ks_needed <= 1 ? 1 : ks_needed <= 2 ? 2 : ks_needed <= 4 ? 4 : ks_needed <= 16 ? 16 : 32;
 
     // all passes of both hemispheres live side by side in the workspace: north passes, then south passes
@@ -580,25 +593,39 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         const int nn = ip < passes[0].size() ? (int)passes[0][ip].size() : 0;
         const int ns = ip < passes[1].size() ? (int)passes[1][ip].size() : 0;
         KernelTimer timer(kScan, st);
-#define HDP_LAUNCH_SCAN(NP, KS)                                                                                          \
-        if (scan_smem > 48 * 1024)                                                                                       \
-            HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NP, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
-        k_scan<NP, KS><<<grid, block, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, sn, nn, ss, ns, \
-                                                       Y, d_is_south, d_out)
-#define HDP_SCAN_KS(NP)                                                    \
+#define HDP_LAUNCH_SCAN(NG, KS, BY)                                                                                      \
+        do {                                                                                                             \
+            if (scan_smem > 48 * 1024)                                                                                   \
+                HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NG, KS, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
+            k_scan<NG, KS, BY><<<scan_grid, kScanWarps * 32, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, \
+                                                                              sn, nn, ss, ns, Y, d_is_south, d_out);     \
+        } while (0)
+#define HDP_SCAN_KS(NG, BY)                                                \
         switch (ks) {                                                      \
-        case 1: HDP_LAUNCH_SCAN(NP, 1); break;                             \
-        case 2: HDP_LAUNCH_SCAN(NP, 2); break;                             \
-        case 4: HDP_LAUNCH_SCAN(NP, 4); break;                             \
-        case 16: HDP_LAUNCH_SCAN(NP, 16); break;                           \
-        default: HDP_LAUNCH_SCAN(NP, 32); break;                           \
+        case 1: HDP_LAUNCH_SCAN(NG, 1, BY); break;                         \
+        case 2: HDP_LAUNCH_SCAN(NG, 2, BY); break;                         \
+        case 4: HDP_LAUNCH_SCAN(NG, 4, BY); break;                         \
+        case 16: HDP_LAUNCH_SCAN(NG, 16, BY); break;                       \
+        default: HDP_LAUNCH_SCAN(NG, 32, BY); break;                       \
         }
-        switch (np) {
-        case 3: HDP_SCAN_KS(3); break;
-        case 4: HDP_SCAN_KS(4); break;
-        case 8: HDP_SCAN_KS(8); break;
-        case 12: HDP_SCAN_KS(12); break;
-        default: HDP_SCAN_KS(16); break;
+        if (bytes) {
+            switch (ng) {                                                  // D <= 32: at most 8 registers of 4
+            case 2: HDP_SCAN_KS(2, true); break;
+            case 3: HDP_SCAN_KS(3, true); break;
+            case 4: HDP_SCAN_KS(4, true); break;
+            case 6: HDP_SCAN_KS(6, true); break;
+            default: HDP_SCAN_KS(8, true); break;
+            }
+        } else {
+            switch (ng) {
+            case 2: HDP_SCAN_KS(2, false); break;
+            case 3: HDP_SCAN_KS(3, false); break;
+            case 4: HDP_SCAN_KS(4, false); break;
+            case 6: HDP_SCAN_KS(6, false); break;
+            case 8: HDP_SCAN_KS(8, false); break;
+            case 12: HDP_SCAN_KS(12, false); break;
+            default: HDP_SCAN_KS(16, false); break;
+            }
         }
 #undef HDP_SCAN_KS
 #undef HDP_LAUNCH_SCAN

@@ -229,6 +229,11 @@ def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, sea
     return out
 
 
+def host_release() -> None:
+    """Free the streams and device buffers the ``*_host`` entry points keep between calls."""
+    _lib.lib().hdp_b200_host_release()
+
+
 def launch_count() -> int:
     return int(_lib.lib().hdp_b200_launch_count())
 

@@ -1,35 +1,109 @@
 // host.cu - the *_host entry points: the same two paths with HOST buffers.
 //
 // Cells are independent in both paths (the reference parallelises over spatial Dask blocks,
-// hdp/threshold.py:161, hdp/metric.py:444), so the host variants cut the cell axis into chunks and run
-// H2D copy -> kernels -> D2H copy of successive chunks on alternating streams: the copies of one chunk
-// overlap the kernels of the other.  Pinned host buffers get full PCIe rate; pageable ones work too.
+// hdp/threshold.py:161, hdp/metric.py:444), so the host variants cut the cell axis into chunks of a few thousand
+// cells and run them through a three-stage pipeline on three streams:
+//
+//     s_in :  H2D copy of chunk i+1 (samples, thresholds, hemisphere flags)
+//     s_k  :  kernels of chunk i
+//     s_out:  D2H copy of the results of chunk i-1
+//
+// with kSlots input and output buffers handed from stage to stage by events, so both PCIe directions and the SMs are
+// busy at the same time and the call runs at the rate of its slowest stage (on B200 + PCIe Gen5: the H2D copy).
+// Index tables are uploaded with the first chunk only and stay in the workspace (thresholds_launch / metrics_launch
+// `tables_resident`), so nothing blocks the host between chunks and the whole call is enqueued ahead of the GPU.
+// Streams, events and device buffers live in a per-device context that is kept between calls (grown on demand;
+// hdp_b200_host_release frees it): cudaMalloc / cudaFree of GB-sized buffers would otherwise cost as much as the copies.
+// Pinned host buffers get the full PCIe rate; pageable ones work but are staged by the driver.
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
 namespace hdp {
 
-constexpr int kSlots = 2;
+int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                      const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
+                      const double *h_q, int P, double *d_out,
+                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident);
+int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                   const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                   const int32_t *h_defs, int D,
+                   const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                   const uint8_t *d_is_south, uint16_t *d_out,
+                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident);
+
+constexpr int kSlots = 3;
+constexpr int kMaxDevices = 64;
 
 struct DeviceBuf {
     void *p = nullptr;
-    ~DeviceBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { return cuda_status(cudaMalloc(&p, bytes ? bytes : 1)); }
+    size_t cap = 0;
+    int reserve(size_t bytes) {                      // grow-only
+        if (bytes <= cap) return HDP_B200_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        HDP_CUDA_TRY(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return HDP_B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct Streams {
-    cudaStream_t s[kSlots] = {};
-    int n = 0;
-    ~Streams() { for (int i = 0; i < n; i++) cudaStreamDestroy(s[i]); }
-    int create() {
-        for (; n < kSlots; n++) HDP_CUDA_TRY(cudaStreamCreateWithFlags(&s[n], cudaStreamNonBlocking));
+struct HostCtx {
+    std::mutex mu;                                   // one host call per device at a time
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t in_ready[kSlots] = {}, k_done[kSlots] = {}, out_done[kSlots] = {};
+    DeviceBuf x[kSlots], aux[kSlots], south[kSlots], out[kSlots], ws;
+
+    int init() {
+        if (ready) return HDP_B200_OK;
+        HDP_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        HDP_CUDA_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        HDP_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; i++) {
+            HDP_CUDA_TRY(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+            HDP_CUDA_TRY(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+            HDP_CUDA_TRY(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+        }
+        ready = true;
         return HDP_B200_OK;
+    }
+    // waits for everything this context has enqueued; returns the first error seen
+    int drain() {
+        int rc = HDP_B200_OK;
+        for (cudaStream_t s : {s_in, s_k, s_out}) {
+            const cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess && rc == HDP_B200_OK) rc = (int)e;
+        }
+        return rc;
+    }
+    void release() {
+        if (ready) {
+            drain();
+            cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out);
+            for (int i = 0; i < kSlots; i++) { cudaEventDestroy(in_ready[i]); cudaEventDestroy(k_done[i]); cudaEventDestroy(out_done[i]); }
+            ready = false;
+        }
+        for (int i = 0; i < kSlots; i++) { x[i].release(); aux[i].release(); south[i].release(); out[i].release(); }
+        ws.release();
     }
 };
 
-// Copies cells [c0, c0+nc) of a host measure array to a dense device buffer and reports the strides of
-// the device copy.  Supported host layouts: cell-contiguous (ld_c == 1) and time-contiguous (ld_t == 1).
+static HostCtx g_ctx[kMaxDevices];
+
+static int current_ctx(HostCtx **ctx)
+{
+    int dev = 0;
+    HDP_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return HDP_B200_ERR_NO_DEVICE;
+    *ctx = &g_ctx[dev];
+    return HDP_B200_OK;
+}
+
+// Enqueues the copy of cells [c0, c0+nc) of a host measure array into a dense device buffer and reports the strides
+// of the device copy.  Supported host layouts: cell-contiguous (ld_c == 1) and time-contiguous (ld_t == 1).
 static int upload_cells(const float *h, int64_t T, int64_t ld_t, int64_t ld_c, int64_t c0, int64_t nc,
                         float *d, int64_t *d_ld_t, int64_t *d_ld_c, cudaStream_t st)
 {
@@ -47,12 +121,18 @@ static int upload_cells(const float *h, int64_t T, int64_t ld_t, int64_t ld_c, i
     return HDP_B200_OK;
 }
 
-static int64_t pick_chunk(int64_t C, size_t bytes_per_cell)
+// Cells per chunk: ~64 MB of input per chunk keeps the pipeline's fill and drain (one chunk each) near one percent of
+// a CMIP-sized call while copy rows stay >= 2 KB and the kernel grids fill the GPU; a multiple of 32 cells (warp = 32
+// cells).  Measured on B200 / PCIe Gen5 (tools/e2e_breakdown.py): 1 024 .. 4 096 cells per chunk are within 2 %.
+static int64_t pick_chunk(int64_t C, size_t in_bytes_per_cell)
 {
-    // ~1.5 GB of device buffers per slot, a multiple of 32 cells, at least 2 chunks when there is enough work
-    int64_t chunk = (int64_t)((size_t)1536 << 20) / (int64_t)std::max<size_t>(bytes_per_cell, 1);
-    chunk = std::max<int64_t>(32, chunk / 32 * 32);
-    if (C > 4096) chunk = std::min(chunk, ((C + 1) / 2 + 31) / 32 * 32);
+    if (const char *e = std::getenv("HDP_B200_HOST_CHUNK_CELLS")) {
+        const int64_t v = std::atoll(e);
+        if (v > 0) return std::min<int64_t>(std::max<int64_t>(32, v / 32 * 32), std::max<int64_t>(C, 1));
+    }
+    int64_t chunk = (int64_t)((size_t)64 << 20) / (int64_t)std::max<size_t>(in_bytes_per_cell, 1);
+    chunk = std::max<int64_t>(512, chunk / 32 * 32);
+    if (C > 2048) chunk = std::min(chunk, ((C + 3) / 4 + 31) / 32 * 32);       // at least 4 chunks once there is work to overlap
     return std::min(chunk, std::max<int64_t>(C, 1));
 }
 
@@ -60,7 +140,23 @@ static int64_t pick_chunk(int64_t C, size_t bytes_per_cell)
 
 using namespace hdp;
 
+// error inside the chunk loop: let the enqueued work finish (it reads and writes the caller's buffers), then report
+#define HDP_HOST_TRY(expr)                                   \
+    do {                                                     \
+        const int _rc = (expr);                              \
+        if (_rc != HDP_B200_OK) { ctx->drain(); return _rc; }\
+    } while (0)
+#define HDP_HOST_CUDA(expr) HDP_HOST_TRY(cuda_status(expr))
+
 extern "C" {
+
+void hdp_b200_host_release(void)
+{
+    for (HostCtx &c : g_ctx) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.ready || c.ws.p || c.x[0].p) c.release();
+    }
+}
 
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
@@ -70,33 +166,43 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
     if (C == 0) return HDP_B200_OK;
     if (!h_temps || !h_out) return HDP_B200_ERR_INVALID;
     if (ld_c != 1 && ld_t != 1) return HDP_B200_ERR_UNSUPPORTED;
+    HostCtx *ctx = nullptr;
+    int rc = current_ctx(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if ((rc = ctx->init())) return rc;
+
     const size_t out_per_cell = (size_t)n_doy * P * sizeof(double);
-    const int64_t chunk = pick_chunk(C, (size_t)T_b * 4 * 2 + out_per_cell);
+    const int64_t chunk = pick_chunk(C, (size_t)T_b * sizeof(float));
     const int64_t dl_t = ld_c == 1 ? chunk : 1, dl_c = ld_c == 1 ? 1 : T_b;
     const size_t ws_bytes = hdp_b200_thresholds_workspace_bytes(chunk, T_b, dl_t, dl_c, n_doy, n_y, W, P);
-    Streams ss;
-    int rc = ss.create();
-    if (rc) return rc;
-    DeviceBuf x[kSlots], out[kSlots], ws[kSlots];
+    if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
     for (int i = 0; i < kSlots; i++) {
-        if ((rc = x[i].alloc((size_t)chunk * T_b * sizeof(float)))) return rc;
-        if ((rc = out[i].alloc((size_t)chunk * out_per_cell))) return rc;
-        if ((rc = ws[i].alloc(ws_bytes))) return rc;
+        if ((rc = ctx->x[i].reserve((size_t)chunk * T_b * sizeof(float)))) return rc;
+        if ((rc = ctx->out[i].reserve((size_t)chunk * out_per_cell))) return rc;
     }
-    int slot = 0;
-    for (int64_t c0 = 0; c0 < C; c0 += chunk, slot = (slot + 1) % kSlots) {
+    int64_t i = 0;
+    for (int64_t c0 = 0; c0 < C; c0 += chunk, i++) {
+        const int slot = (int)(i % kSlots);
         const int64_t nc = std::min(chunk, C - c0);
-        cudaStream_t st = ss.s[slot];
         int64_t a, b;
-        if ((rc = upload_cells(h_temps, T_b, ld_t, ld_c, c0, nc, (float *)x[slot].p, &a, &b, st))) return rc;
-        rc = hdp_b200_thresholds((const float *)x[slot].p, nc, T_b, a, b, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P,
-                                 (double *)out[slot].p, ws[slot].p, ws_bytes, st);
-        if (rc) return rc;
-        HDP_CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)c0 * n_doy * P, out[slot].p, (size_t)nc * out_per_cell,
-                                     cudaMemcpyDeviceToHost, st));
+        // stage 1: samples of this chunk (the slot's previous user must have been consumed by its kernels)
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->k_done[slot], 0));
+        HDP_HOST_TRY(upload_cells(h_temps, T_b, ld_t, ld_c, c0, nc, (float *)ctx->x[slot].p, &a, &b, ctx->s_in));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->in_ready[slot], ctx->s_in));
+        // stage 2: kernels (the slot's previous results must have left for the host)
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_ready[slot], 0));
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
+        HDP_HOST_TRY(thresholds_launch((const float *)ctx->x[slot].p, nc, T_b, a, b, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P,
+                                       (double *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->k_done[slot], ctx->s_k));
+        // stage 3: results
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[slot], 0));
+        HDP_HOST_CUDA(cudaMemcpyAsync(h_out + (size_t)c0 * n_doy * P, ctx->out[slot].p, (size_t)nc * out_per_cell,
+                                      cudaMemcpyDeviceToHost, ctx->s_out));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->out_done[slot], ctx->s_out));
     }
-    for (int i = 0; i < kSlots; i++) HDP_CUDA_TRY(cudaStreamSynchronize(ss.s[i]));
-    return HDP_B200_OK;
+    return ctx->drain();
 }
 
 int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
@@ -109,42 +215,52 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
     if (C == 0 || Y == 0) return HDP_B200_OK;
     if (!h_measure || !h_thr || !h_out) return HDP_B200_ERR_INVALID;
     if (ld_c != 1 && ld_t != 1) return HDP_B200_ERR_UNSUPPORTED;
+    HostCtx *ctx = nullptr;
+    int rc = current_ctx(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if ((rc = ctx->init())) return rc;
+
     const size_t thr_per_cell = (size_t)n_doy * P * sizeof(double);
     const size_t rows = (size_t)4 * P * D * Y;                                 // output rows of C cells each
-    const int64_t chunk = pick_chunk(C, (size_t)T * 4 * 2 + (size_t)T / 8 * P * 2 + thr_per_cell + rows * 2);
+    const int64_t chunk = pick_chunk(C, (size_t)T * sizeof(float) + thr_per_cell);
     const int64_t dl_t = ld_c == 1 ? chunk : 1, dl_c = ld_c == 1 ? 1 : T;
     const size_t ws_bytes = hdp_b200_metrics_workspace_bytes(chunk, T, dl_t, dl_c, n_doy, P, D, Y, h_doy_map);
-    Streams ss;
-    int rc = ss.create();
-    if (rc) return rc;
-    DeviceBuf x[kSlots], thr[kSlots], south[kSlots], out[kSlots], ws[kSlots];
+    if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
     for (int i = 0; i < kSlots; i++) {
-        if ((rc = x[i].alloc((size_t)chunk * T * sizeof(float)))) return rc;
-        if ((rc = thr[i].alloc((size_t)chunk * thr_per_cell))) return rc;
-        if ((rc = south[i].alloc((size_t)chunk))) return rc;
-        if ((rc = out[i].alloc(rows * chunk * sizeof(uint16_t)))) return rc;
-        if ((rc = ws[i].alloc(ws_bytes))) return rc;
+        if ((rc = ctx->x[i].reserve((size_t)chunk * T * sizeof(float)))) return rc;
+        if ((rc = ctx->aux[i].reserve((size_t)chunk * thr_per_cell))) return rc;
+        if ((rc = ctx->south[i].reserve((size_t)chunk))) return rc;
+        if ((rc = ctx->out[i].reserve(rows * chunk * sizeof(uint16_t)))) return rc;
     }
-    int slot = 0;
-    for (int64_t c0 = 0; c0 < C; c0 += chunk, slot = (slot + 1) % kSlots) {
+    int64_t i = 0;
+    for (int64_t c0 = 0; c0 < C; c0 += chunk, i++) {
+        const int slot = (int)(i % kSlots);
         const int64_t nc = std::min(chunk, C - c0);
-        cudaStream_t st = ss.s[slot];
         int64_t a, b;
-        if ((rc = upload_cells(h_measure, T, ld_t, ld_c, c0, nc, (float *)x[slot].p, &a, &b, st))) return rc;
-        HDP_CUDA_TRY(cudaMemcpyAsync(thr[slot].p, h_thr + (size_t)c0 * n_doy * P, (size_t)nc * thr_per_cell,
-                                     cudaMemcpyHostToDevice, st));
-        if (h_is_south) HDP_CUDA_TRY(cudaMemcpyAsync(south[slot].p, h_is_south + c0, (size_t)nc, cudaMemcpyHostToDevice, st));
-        rc = hdp_b200_metrics((const float *)x[slot].p, nc, T, a, b, (const double *)thr[slot].p, n_doy, P, h_doy_map,
-                              h_defs, D, h_season_north, h_season_south, Y,
-                              h_is_south ? (const uint8_t *)south[slot].p : nullptr,
-                              (uint16_t *)out[slot].p, ws[slot].p, ws_bytes, st);
-        if (rc) return rc;
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->k_done[slot], 0));
+        HDP_HOST_TRY(upload_cells(h_measure, T, ld_t, ld_c, c0, nc, (float *)ctx->x[slot].p, &a, &b, ctx->s_in));
+        HDP_HOST_CUDA(cudaMemcpyAsync(ctx->aux[slot].p, h_thr + (size_t)c0 * n_doy * P, (size_t)nc * thr_per_cell,
+                                      cudaMemcpyHostToDevice, ctx->s_in));
+        if (h_is_south)
+            HDP_HOST_CUDA(cudaMemcpyAsync(ctx->south[slot].p, h_is_south + c0, (size_t)nc, cudaMemcpyHostToDevice, ctx->s_in));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->in_ready[slot], ctx->s_in));
+
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_ready[slot], 0));
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
+        HDP_HOST_TRY(metrics_launch((const float *)ctx->x[slot].p, nc, T, a, b, (const double *)ctx->aux[slot].p, n_doy, P, h_doy_map,
+                                    h_defs, D, h_season_north, h_season_south, Y,
+                                    h_is_south ? (const uint8_t *)ctx->south[slot].p : nullptr,
+                                    (uint16_t *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->k_done[slot], ctx->s_k));
+
         // device chunk is [rows, nc]; host array is [rows, C]
-        HDP_CUDA_TRY(cudaMemcpy2DAsync(h_out + c0, (size_t)C * sizeof(uint16_t), out[slot].p, (size_t)nc * sizeof(uint16_t),
-                                       (size_t)nc * sizeof(uint16_t), rows, cudaMemcpyDeviceToHost, st));
+        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[slot], 0));
+        HDP_HOST_CUDA(cudaMemcpy2DAsync(h_out + c0, (size_t)C * sizeof(uint16_t), ctx->out[slot].p, (size_t)nc * sizeof(uint16_t),
+                                        (size_t)nc * sizeof(uint16_t), rows, cudaMemcpyDeviceToHost, ctx->s_out));
+        HDP_HOST_CUDA(cudaEventRecord(ctx->out_done[slot], ctx->s_out));
     }
-    for (int i = 0; i < kSlots; i++) HDP_CUDA_TRY(cudaStreamSynchronize(ss.s[i]));
-    return HDP_B200_OK;
+    return ctx->drain();
 }
 
 }  // extern "C"

@@ -405,13 +405,14 @@ static bool bad_dims(int64_t C, int64_t T, int n_doy, int P)
 // Runs k_hot_words; on success *plan_out/*L_out describe what lives in the workspace.
 static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                          const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
-                         int Y, void *ws, size_t ws_bytes, cudaStream_t st, WordPlan &plan, Layout &L)
+                         int Y, void *ws, size_t ws_bytes, cudaStream_t st, WordPlan &plan, Layout &L,
+                         int64_t carve_cells = 0, bool tables_resident = false)
 {
     int rc = build_words(h_doy_map, T, n_doy, plan);
     if (rc != HDP_B200_OK) return rc;
     const int K = (int)plan.words.size();
     const bool need_norm = ld_c != 1;
-    L = carve(ws, ws_bytes, C, T, need_norm, K, n_doy, P, Y);
+    L = carve(ws, ws_bytes, std::max(C, carve_cells), T, need_norm, K, n_doy, P, Y);
     if (ws == nullptr || L.total > ws_bytes) return HDP_B200_ERR_WORKSPACE;
     if (C == 0 || T == 0) return HDP_B200_OK;
     const float *x = d_measure;
@@ -421,9 +422,9 @@ static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t l
         x = L.xn;
         ld_t = C;
     }
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.words, plan.words.data(), sizeof(int4) * K, cudaMemcpyHostToDevice, st));
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_start, plan.blk_start.data(), sizeof(int) * plan.blk_start.size(), cudaMemcpyHostToDevice, st));
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_words, plan.blk_words.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.words, plan.words.data(), sizeof(int4) * K, cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_start, plan.blk_start.data(), sizeof(int) * plan.blk_start.size(), cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.blk_words, plan.blk_words.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
 
     const int pg = pick_pg(P);
     const int Ppad = (P + pg - 1) / pg * pg;
@@ -458,48 +459,13 @@ static void clamp_season(int64_t a, int64_t b, int64_t T, int &lo, int &hi)
     lo = (int)a; hi = (int)b;
 }
 
-}  // namespace hdp
-
-using namespace hdp;
-
-extern "C" {
-
-size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                                        int n_doy, int P, int D, int Y, const int32_t *h_doy_map)
-{
-    (void)ld_t; (void)D;
-    if (bad_dims(C, T, n_doy, P) || Y < 0) return 0;
-    const int64_t K = h_doy_map ? count_words(h_doy_map, T) : words_upper_bound(T, n_doy);
-    return carve(nullptr, 0, C, T, ld_c != 1, K, n_doy, P, Y).total;
-}
-
-int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                      const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
-                      uint8_t *d_mask, void *d_workspace, size_t workspace_bytes, void *stream)
-{
-    if (bad_dims(C, T, n_doy, P) || !h_doy_map && T > 0) return HDP_B200_ERR_INVALID;
-    if (C > 0 && T > 0 && (!d_measure || !d_thr || !d_mask)) return HDP_B200_ERR_INVALID;
-    if (P > HDP_B200_MAX_PERCENTILES) return HDP_B200_ERR_UNSUPPORTED;
-    cudaStream_t st = (cudaStream_t)stream;
-    WordPlan plan;
-    Layout L;
-    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, 0, d_workspace, workspace_bytes, st, plan, L);
-    if (rc != HDP_B200_OK || C == 0 || T == 0) return rc;
-    const int K = (int)plan.words.size();
-    dim3 grid((unsigned)((C + 255) / 256), (unsigned)K);
-    if (K > 65535) return HDP_B200_ERR_UNSUPPORTED;
-    KernelTimer timer(kUnpackMask, st);
-    k_unpack_mask<<<grid, 256, 0, st>>>(L.hot, C, T, P, K, L.words, d_mask);
-    HDP_LAUNCH_CHECK();
-    return HDP_B200_OK;
-}
-
-int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                     const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
-                     const int32_t *h_defs, int D,
-                     const int32_t *h_season_north, const int32_t *h_season_south, int Y,
-                     const uint8_t *d_is_south, uint16_t *d_out,
-                     void *d_workspace, size_t workspace_bytes, void *stream)
+// The whole of hdp_b200_metrics; carve_cells / tables_resident as in thresholds_launch (threshold.cu).
+int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                   const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                   const int32_t *h_defs, int D,
+                   const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                   const uint8_t *d_is_south, uint16_t *d_out,
+                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident)
 {
     if (bad_dims(C, T, n_doy, P) || D <= 0 || Y < 0) return HDP_B200_ERR_INVALID;
     if ((T > 0 && !h_doy_map) || !h_defs || (Y > 0 && (!h_season_north || !h_season_south))) return HDP_B200_ERR_INVALID;
@@ -532,7 +498,8 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
 
     WordPlan plan;
     Layout L;
-    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, Y, d_workspace, workspace_bytes, st, plan, L);
+    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, Y, d_workspace, workspace_bytes, st, plan, L,
+                            carve_cells, tables_resident);
     if (rc != HDP_B200_OK || C == 0 || Y == 0) return rc;
     const int K = (int)plan.words.size();
 
@@ -561,7 +528,7 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         for (int i = 0; i < D; i++) if (h_defs[3 * i] <= l) lut[l] |= 1u << i;
     for (int g = 0; g < tabs.brk_len; g++)
         for (int i = 0; i < D; i++) if (h_defs[3 * i + 1] < g) lut[tabs.ge_len + g] |= 1u << i;
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
     const uint32_t *ge_tab = L.lut, *brk_tab = L.lut + tabs.ge_len;
     const size_t scan_smem = (lut.size() + (size_t)K + 2) * sizeof(uint32_t);
     if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~45 000 hot words (~4 000 years of daily data)
@@ -586,7 +553,7 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
             off[h].push_back(tab.size());
             for (const Season &s : pass) tab.push_back(make_int4(s.a, s.b, s.row, 0));
         }
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.seasons, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.seasons, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice, st));
     for (size_t ip = 0; ip < n_pass; ip++) {
         const int4 *sn = ip < passes[0].size() ? L.seasons + off[0][ip] : L.seasons;
         const int4 *ss = ip < passes[1].size() ? L.seasons + off[1][ip] : L.seasons;
@@ -632,6 +599,53 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
         HDP_LAUNCH_CHECK();
     }
     return HDP_B200_OK;
+}
+
+}  // namespace hdp
+
+using namespace hdp;
+
+extern "C" {
+
+size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                                        int n_doy, int P, int D, int Y, const int32_t *h_doy_map)
+{
+    (void)ld_t; (void)D;
+    if (bad_dims(C, T, n_doy, P) || Y < 0) return 0;
+    const int64_t K = h_doy_map ? count_words(h_doy_map, T) : words_upper_bound(T, n_doy);
+    return carve(nullptr, 0, C, T, ld_c != 1, K, n_doy, P, Y).total;
+}
+
+int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                      const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                      uint8_t *d_mask, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (bad_dims(C, T, n_doy, P) || !h_doy_map && T > 0) return HDP_B200_ERR_INVALID;
+    if (C > 0 && T > 0 && (!d_measure || !d_thr || !d_mask)) return HDP_B200_ERR_INVALID;
+    if (P > HDP_B200_MAX_PERCENTILES) return HDP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    WordPlan plan;
+    Layout L;
+    int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, 0, d_workspace, workspace_bytes, st, plan, L);
+    if (rc != HDP_B200_OK || C == 0 || T == 0) return rc;
+    const int K = (int)plan.words.size();
+    dim3 grid((unsigned)((C + 255) / 256), (unsigned)K);
+    if (K > 65535) return HDP_B200_ERR_UNSUPPORTED;
+    KernelTimer timer(kUnpackMask, st);
+    k_unpack_mask<<<grid, 256, 0, st>>>(L.hot, C, T, P, K, L.words, d_mask);
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
+}
+
+int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
+                     const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
+                     const int32_t *h_defs, int D,
+                     const int32_t *h_season_north, const int32_t *h_season_south, int Y,
+                     const uint8_t *d_is_south, uint16_t *d_out,
+                     void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    return metrics_launch(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, h_defs, D, h_season_north, h_season_south, Y,
+                          d_is_south, d_out, d_workspace, workspace_bytes, stream, C, false);
 }
 
 }  // extern "C"

@@ -1207,26 +1207,13 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
 static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
 static int g_force_ranked = 0;
 
-}  // namespace hdp
-
-using namespace hdp;
-
-extern "C" {
-
-void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; }
-
-size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
-                                           int n_doy, int n_y, int W, int P)
-{
-    (void)ld_t;
-    if (bad_dims(C, T_b, n_doy, n_y, W, P)) return 0;
-    return carve_thr(nullptr, 0, C, T_b, ld_c != 1, n_doy, n_y, W).total;
-}
-
-int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
-                        const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
-                        const double *h_q, int P, double *d_out,
-                        void *d_workspace, size_t workspace_bytes, void *stream)
+// The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
+// capacity so that every chunk sees the tables at the same place) and `tables_resident` skips the table uploads when
+// the previous call on this workspace and stream used identical tables.
+int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                      const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
+                      const double *h_q, int P, double *d_out,
+                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident)
 {
     if (bad_dims(C, T_b, n_doy, n_y, W, P) || !h_time_index || !h_win_rows || !h_q) return HDP_B200_ERR_INVALID;
     if (C > 0 && (!d_temps || !d_out)) return HDP_B200_ERR_INVALID;
@@ -1247,7 +1234,7 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
 
     cudaStream_t st = (cudaStream_t)stream;
     const bool need_norm = ld_c != 1;
-    ThrLayout L = carve_thr(d_workspace, workspace_bytes, C, T_b, need_norm, n_doy, n_y, W);
+    ThrLayout L = carve_thr(d_workspace, workspace_bytes, std::max(C, carve_cells), T_b, need_norm, n_doy, n_y, W);
     if (!d_workspace || L.total > workspace_bytes) return HDP_B200_ERR_WORKSPACE;
     const float *x = d_temps;
     if (need_norm) {
@@ -1256,7 +1243,7 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
         x = L.xn;
         ld_t = C;
     }
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
 
     // plans depend on the tables only: keep the last one (calls are serialised on the host side; the launches are asynchronous)
     static std::mutex plan_mu;
@@ -1283,9 +1270,9 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
     if (seg.usable && !g_force_generic && !g_force_ranked) {
         SelTable sel;
         fill_sel(sel, b, h_q, P);
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_time, seg.seg_time.data(), sizeof(int) * seg.seg_time.size(), cudaMemcpyHostToDevice, st));
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_ne, seg.seg_ne.data(), sizeof(int) * seg.seg_ne.size(), cudaMemcpyHostToDevice, st));
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_rng, seg.doy_rng.data(), seg.doy_rng.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_time, seg.seg_time.data(), sizeof(int) * seg.seg_time.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_ne, seg.seg_ne.data(), sizeof(int) * seg.seg_ne.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_rng, seg.doy_rng.data(), seg.doy_rng.size(), cudaMemcpyHostToDevice, st));
         static bool attr_done = false;
         const size_t smem = (size_t)kSegWarps * kSegWarpBytes;
         if (!attr_done) {
@@ -1305,9 +1292,9 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
         return HDP_B200_OK;
     }
     if (plan.usable && !g_force_generic) {
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.op_off, plan.op_off.data(), sizeof(int) * plan.op_off.size(), cudaMemcpyHostToDevice, st));
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
-        HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_dup, plan.doy_dup.data(), plan.doy_dup.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.op_off, plan.op_off.data(), sizeof(int) * plan.op_off.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
+        if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_dup, plan.doy_dup.data(), plan.doy_dup.size(), cudaMemcpyHostToDevice, st));
         HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
         KernelTimer timer(kThrRanked, st);
         k_thr_ranked<<<(unsigned)C, kRankedThreads, plan.smem, st>>>(x, T_b, ld_t, L.time_index, E, n_y, n_doy, (int)b,
@@ -1318,7 +1305,7 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
     }
 
     // generic path: any table, any multiplicity
-    HDP_CUDA_TRY(cudaMemcpyAsync(L.win_rows, h_win_rows, sizeof(int) * (size_t)n_doy * W, cudaMemcpyHostToDevice, st));
+    if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.win_rows, h_win_rows, sizeof(int) * (size_t)n_doy * W, cudaMemcpyHostToDevice, st));
     int b_pad_log2 = 1;
     while ((1 << b_pad_log2) < b) b_pad_log2++;
     const int b_pad = 1 << b_pad_log2;
@@ -1332,6 +1319,31 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
     k_thr_generic<<<grid, 256, smem, st>>>(x, C, T_b, ld_t, L.time_index, L.win_rows, n_doy, n_y, W, qt, P, NC, b_pad_log2, d_out);
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;
+}
+
+}  // namespace hdp
+
+using namespace hdp;
+
+extern "C" {
+
+void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; }
+
+size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                                           int n_doy, int n_y, int W, int P)
+{
+    (void)ld_t;
+    if (bad_dims(C, T_b, n_doy, n_y, W, P)) return 0;
+    return carve_thr(nullptr, 0, C, T_b, ld_c != 1, n_doy, n_y, W).total;
+}
+
+int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
+                        const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
+                        const double *h_q, int P, double *d_out,
+                        void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    return thresholds_launch(d_temps, C, T_b, ld_t, ld_c, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P, d_out,
+                             d_workspace, workspace_bytes, stream, C, false);
 }
 
 }  // extern "C"

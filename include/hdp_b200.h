@@ -13,7 +13,7 @@
  *                                    heatwave_frequency/number/duration/average :63-172)
  *                                   + compute_heatwave_metrics_wrapper     hdp/metric.py:344-369
  *   hdp_b200_hot_days     replaces  indicate_hot_days                     hdp/metric.py:280-301   (parity checks)
- *   *_host variants       the same calls with HOST buffers (chunked H2D -> kernels -> D2H inside).
+ *   *_host variants       the same calls with HOST buffers (cell chunks pipelined H2D -> kernels -> D2H on three streams).
  *
  * Conventions
  *   - Pointers named d_*  are DEVICE pointers owned by the caller (e.g. torch tensors).
@@ -22,7 +22,8 @@
  *   - Every device call takes a cudaStream_t (as void*), enqueues its work on it and returns without
  *     synchronising the device (small pageable-host table uploads are the only host-blocking step).
  *   - No allocation inside the device calls: scratch comes from the caller-sized workspace
- *     (hdp_b200_*_workspace_bytes).  The *_host variants allocate and free their own device buffers.
+ *     (hdp_b200_*_workspace_bytes).  The *_host variants own their device buffers
+ *     (kept between calls, see hdp_b200_host_release).
  *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = one of the HDP_B200_ERR_* codes.  Nothing throws.
  *   - Element (t, c) of a measure array lives at base[t*ld_t + c*ld_c] (strides in ELEMENTS).
  *     The fast path is time-major, cell-contiguous (ld_c == 1); any other layout is first
@@ -120,6 +121,10 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
                           const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                           const uint8_t *h_is_south,
                           uint16_t *h_out);
+
+/* The *_host variants keep their streams, events and device buffers (grown on demand) in a per-device context between
+ * calls; this frees them.  Safe to call at any time no *_host call is running. */
+void hdp_b200_host_release(void);
 
 /* Hot-day mask only (parity checks): d_mask u8 [P, T, C], 1 where measure > threshold[doy_map[t]]
  * compared in double precision, NaN -> 0 (metric.py:280-301).  Same workspace size as hdp_b200_metrics. */

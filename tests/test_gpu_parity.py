@@ -253,3 +253,34 @@ def test_metrics_tiny_and_empty(core):
     thr = torch.zeros((0, 1, 2), dtype=torch.float64, device="cuda")
     out = core.metrics_array(x, thr, np.zeros(10, int), [[3, 0, 0]], [[0, 10]], [[0, 10]])
     assert tuple(out.shape) == (4, 2, 1, 1, 0)
+
+
+# ------------------------------------------------------------------------------------------ host pipeline
+@pytest.mark.parametrize("chunk", ["32", "64", "96"])
+def test_host_pipeline_many_chunks(core, monkeypatch, chunk):
+    # the *_host entry points with cell chunks far smaller than the grid: more chunks than pipeline slots, a ragged last
+    # chunk, tables uploaded with the first chunk only; both host layouts; must equal the device-resident path bit for bit
+    from hdp_b200 import _tables as tb
+    monkeypatch.setenv("HDP_B200_HOST_CHUNK_CELLS", chunk)
+    rng = np.random.default_rng(23)
+    base_ax = tb.TimeAxis.date_range("1961-01-01", "1966-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2008-12-31", "noleap")
+    wt = tb.window_tables(base_ax.dayofyr, 7)
+    C = 299
+    season = lambda ax: 15 + 10 * np.sin(2 * np.pi * (ax.dayofyr[:, None] - 110) / 365)
+    xb = (season(base_ax) + 3 * rng.standard_normal((len(base_ax), C))).astype(np.float32)
+    xr = (season(run_ax) + 3 * rng.standard_normal((len(run_ax), C)) + 2).astype(np.float32)
+    q = np.arange(0.9, 1.0, 0.01)
+    thr_d = core.thresholds_array(dev(xb), wt, q)
+    thr_h = core.thresholds_host(xb, wt, q)
+    assert bits_equal(thr_h, thr_d.cpu().numpy())
+    assert bits_equal(core.thresholds_host(np.ascontiguousarray(xb.T).T, wt, q), thr_h)
+    st = tb.hemisphere_ranges(run_ax)
+    is_south = (rng.random(C) < 0.5).astype(np.uint8)
+    args = (tb.doy_map(run_ax.dayofyr), [[3, 0, 0], [3, 1, 1], [4, 0, 0], [4, 1, 1], [5, 0, 0], [5, 1, 1]], st.north, st.south, is_south)
+    out_d = core.metrics_array(dev(xr), thr_d, *args).cpu().numpy()
+    assert np.array_equal(core.metrics_host(xr, thr_h, *args), out_d)
+    assert np.array_equal(core.metrics_host(np.ascontiguousarray(xr.T).T, thr_h, *args), out_d)
+    assert np.array_equal(core.metrics_host(xr, thr_h, *args[:-1], None), core.metrics_array(dev(xr), thr_d, *args[:-1], None).cpu().numpy())
+    core.host_release()
+    assert bits_equal(core.thresholds_host(xb, wt, q), thr_h)          # the context comes back after a release

@@ -32,16 +32,46 @@ namespace hdp {
 // ----------------------------------------------------------------------------------------------------
 constexpr int kTileCells = 32;
 constexpr int kTileDoy = 32;
+constexpr int kHotYears = 2;  // words (years) a warp compares against one register copy of the day's thresholds
+constexpr int kHotDays = 16;  // days of each of them whose samples are in flight together
 constexpr int kTilePad = 33;   // [.. ][33]: conflict-free both for the e-major fill and the lane-major reads
 
+// m |= bit where v > t (false when either side is NaN): one compare and one predicated OR with an immediate
+__device__ __forceinline__ void or_if_gt(uint32_t &m, float v, float t, uint32_t bit)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(v), "f"(t), "r"(bit));
+}
+
+template <int PG, int J0>
+__device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const float *const (&xp)[kHotYears], const int (&jo)[kHotYears],
+                                         const int (&nb)[kHotYears], int64_t ld_t, const float *ts)
+{
+    float v[kHotYears][kHotDays];
+#pragma unroll
+    for (int y = 0; y < kHotYears; y++)
+#pragma unroll
+        for (int j = 0; j < kHotDays; j++)                 // NaN = never hot: days outside the word
+            v[y][j] = (unsigned)(J0 + j - jo[y]) < (unsigned)nb[y] ? __ldg(xp[y] + (int64_t)(J0 + j) * ld_t) : __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int j = 0; j < kHotDays; j++) {
+        float t[PG];
+#pragma unroll
+        for (int q = 0; q < PG; q++) t[q] = ts[((J0 + j) * PG + q) * kTilePad];
+#pragma unroll
+        for (int y = 0; y < kHotYears; y++)
+#pragma unroll
+            for (int q = 0; q < PG; q++) or_if_gt(m[y][q], v[y][j], t[q], 1u << (J0 + j));
+    }
+}
+
 template <int PG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PG <= 10 ? 3 : 2)
 k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
             const double *__restrict__ thr, int n_doy, int P,
             const int4 *__restrict__ words, const int *__restrict__ blk_start, const int *__restrict__ blk_words,
             int K, uint32_t *__restrict__ hot)
 {
-    extern __shared__ float thr_s[];                      // [32 doy][Ppad][33]
+    extern __shared__ float thr_s[];                      // [percentile group][32 doy][PG][33]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int db = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * kTileCells;
@@ -56,34 +86,46 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
         float v = __int_as_float(0x7f800000);             // +inf: never exceeded (padding percentiles / days)
         if (c0 + cell < C && j < nd && p < P)
             v = __double2float_rd(thr[((c0 + cell) * n_doy + (db * kTileDoy + j)) * (int64_t)P + p]);
-        thr_s[e * kTilePad + cell] = v;
+        const int g = p / PG, q = p - g * PG;
+        thr_s[((g * kTileDoy + j) * PG + q) * kTilePad + cell] = v;
     }
     __syncthreads();
 
     const int64_t c = c0 + lane;
     if (c >= C) return;
+    // A warp takes kHotYears words (= years of this day-of-year block) at a time.  It first puts kHotDays days of each
+    // of them in flight (kHotYears * kHotDays independent 128-byte loads per warp), then compares them against the days'
+    // thresholds, which are read from shared memory into registers once per kHotYears samples.  Bits are collected at
+    // the day's position inside the 32-day block (an immediate) and shifted to the word's own origin when stored.
     const int w_begin = blk_start[db], w_end = blk_start[db + 1];
-    for (int i = w_begin + warp; i < w_end; i += 8) {
-        const int k = blk_words[i];
-        const int4 w = words[k];                           // {t0, nbits, doy of bit 0, -}
-        const int nb = w.y, jo = w.z & (kTileDoy - 1);
-        const float *xp = x + (int64_t)w.x * ld_t + c;
-        for (int pg = 0; pg < Ppad; pg += PG) {
-            uint32_t m[PG];
+    for (int i0 = w_begin + warp * kHotYears; i0 < w_end; i0 += 8 * kHotYears) {
+        int kk[kHotYears], jo[kHotYears], nb[kHotYears];
+        const float *xp[kHotYears];
+        int j_hi = 0;
 #pragma unroll
-            for (int q = 0; q < PG; q++) m[q] = 0u;
-            const float *ts = thr_s + (jo * Ppad + pg) * kTilePad + lane;
-#pragma unroll 4
-            for (int j = 0; j < nb; j++) {
-                const float v = xp[(int64_t)j * ld_t];
-                const uint32_t bit = 1u << j;
+        for (int y = 0; y < kHotYears; y++) {
+            const bool live = i0 + y < w_end;
+            kk[y] = blk_words[live ? i0 + y : i0];
+            const int4 w = words[kk[y]];                   // {t0, nbits, doy of bit 0, -}
+            jo[y] = w.z & (kTileDoy - 1);
+            nb[y] = live ? w.y : 0;
+            xp[y] = x + ((int64_t)w.x - jo[y]) * ld_t + c; // day jd of the block is sample xp[y][jd * ld_t]
+            if (live) j_hi = max(j_hi, jo[y] + nb[y]);
+        }
+        for (int pg = 0; pg < Ppad; pg += PG) {
+            uint32_t m[kHotYears][PG];
+#pragma unroll
+            for (int y = 0; y < kHotYears; y++)
+#pragma unroll
+                for (int q = 0; q < PG; q++) m[y][q] = 0u;
+            const float *ts = thr_s + (size_t)(pg / PG) * (kTileDoy * PG * kTilePad) + lane;
+            hot_half<PG, 0>(m, xp, jo, nb, ld_t, ts);
+            if (j_hi > kHotDays) hot_half<PG, kHotDays>(m, xp, jo, nb, ld_t, ts);      // warp-uniform
+#pragma unroll
+            for (int y = 0; y < kHotYears; y++)
 #pragma unroll
                 for (int q = 0; q < PG; q++)
-                    if (v > ts[(j * Ppad + q) * kTilePad]) m[q] |= bit;     // NaN on either side -> false
-            }
-#pragma unroll
-            for (int q = 0; q < PG; q++)
-                if (pg + q < P) hot[((int64_t)(pg + q) * K + k) * C + c] = m[q];
+                    if (nb[y] > 0 && pg + q < P) hot[((int64_t)(pg + q) * K + kk[y]) * C + c] = m[y][q] >> jo[y];
         }
     }
 }

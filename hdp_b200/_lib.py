@@ -30,6 +30,7 @@ SIGNATURES = {
     "hdp_b200_metrics": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p, _p, _sz, _p]),
     "hdp_b200_metrics_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p]),
     "hdp_b200_host_release": (None, []),
+    "hdp_b200_metrics_run_filter": (None, [_int]),
     "hdp_b200_timing_enable": (None, [_int]),
     "hdp_b200_timing_read": (_int, [_p, _p, _int]),
     "hdp_b200_hot_days": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _p, _sz, _p]),

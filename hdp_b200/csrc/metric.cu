@@ -150,31 +150,44 @@ k_unpack_mask(const uint32_t *__restrict__ hot, int64_t C, int64_t T, int P, int
 // ----------------------------------------------------------------------------------------------------
 // k_scan
 // ----------------------------------------------------------------------------------------------------
-// One thread per (cell, percentile); lanes = 32 neighbouring cells.  Every definition's state machine
-// (reference index_heatwaves, hdp/metric.py:39-58) is advanced BIT-PARALLEL: bit i of each state word
-// belongs to definition i, so one hot run costs the same logic instructions for 1 or 32 definitions.
-//   inhw        bit i = in_heatwave of definition i
-//   rem[k]      bit-sliced down counter: remaining subsequent events = max_subs - sub_events
-//   fresh       bit i = the next labelled run of definition i starts a heatwave id not yet seen in the open season
-// The loop is FLAT and lane-asynchronous: in one step a lane pops one hot run of its current word (if it has one) and
-// then, if the word is used up, moves on to its next word.  Both halves are predicated, so the warp stays converged on
-// one short body whatever the lanes' run patterns are; a lane needs max(1, runs) steps per word.
-// Season accumulators are packed SIMD-in-register: four definitions per register (8-bit lanes) when no season is longer
-// than 255 days, else two (16-bit lanes): cnt (days of the current id in the open season), HWF, HWN, HWD.  Seasons are
-// closed with the whole warp converged on the stores.
-//
-// Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
-// (the host splits overlapping tables into several passes, one launch each).
+static int g_scan_filter = 1;        // test hook (hdp_b200_metrics_run_filter): 0 = k_scan queues every run
+
 struct ScanTables {
     uint32_t max_subs_plane[32];     // bit k of max_subs of every definition (bit-sliced constants)
     int ge_len, brk_len;             // table lengths: max(min_dur) + 2, max(max_break) + 2
+    int f_on, f_lmin, f_bmax;        // run filter: on/off, min over definitions of min_dur, max over definitions of max_break
 };
 
 constexpr int kScanWarps = 8;
+constexpr int kScanQ = 16;                                       // queued words per lane (power of two)
+constexpr int kScanQueueWords = 3 * kScanQ * 32;                  // u32 per warp: run starts, run ends, first day of the word
 
-// NG accumulator registers per metric; kBytes: 4 definitions per register (8-bit lanes), else 2 (16-bit lanes)
+// k_scan.  One warp per (32 neighbouring cells, percentile), one lane per cell.  Two alternating phases:
+//
+//  A (warp-synchronous over the hot words, in time order): the lanes read word k of their cells (one coalesced
+//    load, prefetched four words ahead), DROP THE RUNS THAT CANNOT MATTER and queue what is left of the word, as run
+//    start / run end bit masks, in a per-lane ring buffer in shared memory.  A run shorter than every definition's
+//    min_duration whose preceding break is longer than every definition's max_break only clears in_heatwave for all
+//    definitions (reference index_heatwaves, hdp/metric.py:43-58: branch A needs the length, C and D need
+//    in_heatwave) - and the longer break the next run then sees does exactly the same, so such runs are removed with
+//    bit operations on the word and its neighbours (long = member of min_duration consecutive hot days; near = the
+//    run starts within max_break + 1 days of a hot day; keep = long | near, flood-filled over the run by an add).
+//    Where a neighbouring word is not known yet the run is kept.  Words without a surviving run start or end are
+//    not queued at all.
+//  B (lane-asynchronous): every lane pops the runs of its own queue and advances ALL definitions' state machines
+//    BIT-PARALLEL: bit i of each state word belongs to definition i, so one run costs the same for 1 or 32 definitions.
+//      inhw        bit i = in_heatwave of definition i
+//      rem[k]      bit-sliced down counter: remaining subsequent events = max_subs - sub_events
+//      fresh       bit i = the next labelled run of definition i starts a heatwave id not yet seen in the open season
+//    Season accumulators are packed SIMD-in-register: four definitions per register (8-bit lanes) when no season is
+//    longer than 255 days, else two (16-bit lanes): cnt (days of the current id in the open season), HWF, HWN, HWD.
+//    A lane stops at the first run that starts after its open season; when every lane has stopped the season is closed
+//    with the whole warp converged on the stores.
+//
+// Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
+// (the host splits overlapping tables into several passes, one launch each).
 template <int NG, int KS, bool kBytes>
-__global__ void __launch_bounds__(kScanWarps * 32, NG <= 4 && KS <= 2 ? 4 : 2)
+__global__ void __launch_bounds__(kScanWarps * 32, 3)
 k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
        int P, int D, const __grid_constant__ ScanTables tabs, const uint32_t *__restrict__ ge_tab, const uint32_t *__restrict__ brk_tab,
        const int4 *__restrict__ seasons_north, int n_north, const int4 *__restrict__ seasons_south, int n_south, int Y,
@@ -183,13 +196,14 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     constexpr int PER = kBytes ? 4 : 2, BITS = kBytes ? 8 : 16;
     constexpr uint32_t LANE_MASK = kBytes ? 0xffu : 0xffffu;
     extern __shared__ uint32_t smem_scan[];
-    uint32_t *ge_s = smem_scan;                                   // [ge_len]  definitions with min_dur <= len
+    uint32_t *queues = smem_scan;                                 // [warps][3][kScanQ][32]
+    uint32_t *ge_s = queues + kScanWarps * kScanQueueWords;       // [ge_len]  definitions with min_dur <= len
     uint32_t *brk_s = ge_s + tabs.ge_len;                         // [brk_len] definitions with max_break < gap
-    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 2] first day of every hot word; word K is a virtual cold day at T
+    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 3] first day of every hot word; word K is a virtual cold day at T
     const int tid = threadIdx.x, nthreads = kScanWarps * 32;
     for (int i = tid; i < tabs.ge_len; i += nthreads) ge_s[i] = ge_tab[i];
     for (int i = tid; i < tabs.brk_len; i += nthreads) brk_s[i] = brk_tab[i];
-    for (int i = tid; i <= K + 1; i += nthreads) word_t0[i] = i < K ? words[i].x : T + (i - K);
+    for (int i = tid; i <= K + 2; i += nthreads) word_t0[i] = i < K ? words[i].x : T + (i - K);
     __syncthreads();
 
     // warp -> (group of 32 cells, percentile): every warp of the grid has work
@@ -200,6 +214,7 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     if (cg * 32 >= C) return;                                     // warp-uniform
     const bool alive = cg * 32 + lane < C;                        // lanes past the last cell shadow it (the warp votes with all 32 lanes)
     const int64_t c = alive ? cg * 32 + lane : C - 1;
+    uint32_t *q_st = queues + (tid >> 5) * kScanQueueWords + lane, *q_en = q_st + kScanQ * 32, *q_t0 = q_en + kScanQ * 32;
 
     const bool south = is_south != nullptr && is_south[c] != 0;
     const int4 *seas = south ? seasons_south : seasons_north;
@@ -260,84 +275,145 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
         }
     };
 
-    int prev_e = -(1 << 29);      // end of the previous hot run
-    int run_start = -1;           // start of the hot run still open at the end of the previous word
+    // ---- phase A state ----
     const uint32_t *hp = hot + (int64_t)p * K * C + c;
-    const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
+    int k_ext = 0;                                                // next word to extract (warp-uniform); word K is the virtual one
+    uint32_t w0 = K > 0 ? hp[0] : 0u, w1 = K > 1 ? hp[C] : 0u, w2 = K > 2 ? hp[2 * C] : 0u, w3 = K > 3 ? hp[3 * C] : 0u;
+    const uint32_t *hp_ahead = hp + 4 * C;                        // word k_ext + 4
+    uint32_t tail = 0u, a_tail = 0u;                              // hot days / `long` seeds of the 32 days before word k_ext (bit 31 = yesterday)
+    uint32_t carry_keep = 0u, open_f = 0u;                        // a kept `near` run / any kept run reaches the end of the previous word
+    uint32_t qr = 0u, qw = 0u;                                    // ring buffer read / write counters
+    const bool f_on = tabs.f_on != 0;
+    const int f_lmin = tabs.f_lmin, f_bmax = tabs.f_bmax;
 
-    int k = -1, t0 = 0;
+    auto extract = [&](int n_words, bool live) {
+        for (int i = 0; i < n_words; i++) {
+            const int k = k_ext;
+            const int t0 = word_t0[k], nb = word_t0[k + 1] - t0;   // (1 for the virtual word K: a cold day closing a run at the series end)
+            const uint32_t cur = k < K ? w0 : 0u;
+            const uint32_t vmask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            uint32_t keep = cur;
+            if (f_on) {
+                // E = the 64 days starting at this word (lo, hi): the next word follows at bit nb; days that are not
+                // known yet count as hot, days past the end of the series are cold
+                const bool last = k + 1 >= K;
+                const int nb1 = word_t0[k + 2] - word_t0[k + 1];
+                const uint32_t fut = last ? 0u : (w1 | (nb1 == 32 ? 0u : 0xffffffffu << nb1));
+                uint32_t lo = cur, hi = fut;
+                if (nb < 32) {                                     // warp-uniform
+                    lo = cur | (fut << nb);
+                    hi = (fut >> (32 - nb)) | (last ? 0u : 0xffffffffu << nb);
+                }
+                uint32_t a = lo;                                   // a_j: days j .. j + lmin - 1 are all hot
+                for (int j = 1; j < f_lmin; j++) a &= __funnelshift_r(lo, hi, j);
+                a &= vmask;
+                uint32_t b = a;                                    // b_j: day j belongs to lmin consecutive hot days
+                for (int j = 1; j < f_lmin; j++) b |= __funnelshift_l(a_tail, a, j);
+                uint32_t near = 0u;                                // near_j: one of the days j - 2 .. j - bmax - 1 is hot
+                for (int j = 2; j <= f_bmax + 1; j++) near |= __funnelshift_l(tail, cur, j);
+                const uint32_t prev = __funnelshift_l(tail, cur, 1);                   // day j - 1 is hot
+                const uint32_t ns = (cur & ~prev & near) | (carry_keep & cur & 1u);
+                const uint32_t fill = ((cur + ns) ^ cur) & cur;    // the whole run above every kept run start
+                keep = (b | fill) & cur;
+                carry_keep = (fill >> (nb - 1)) & 1u;
+                tail = nb == 32 ? cur : __funnelshift_r(tail, cur, nb);
+                a_tail = nb == 32 ? a : __funnelshift_r(a_tail, a, nb);
+            }
+            const uint32_t prevk = (keep << 1) | open_f;           // bit i = day i - 1 is a kept hot day
+            const uint32_t st = keep & ~prevk, en = ~keep & prevk & vmask;
+            open_f = (keep >> (nb - 1)) & 1u;
+            if (live && (st | en) != 0u) {
+                const uint32_t slot = (qw & (kScanQ - 1)) * 32;
+                q_st[slot] = st; q_en[slot] = en; q_t0[slot] = (uint32_t)t0;
+                qw++;
+            }
+            w0 = w1; w1 = w2; w2 = w3;
+            if (k + 4 < K) w3 = *hp_ahead;
+            if (k + 4 + kScanQ < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp_ahead + (int64_t)kScanQ * C));   // the next burst's words
+            hp_ahead += C;
+            k_ext++;
+        }
+    };
+
+    // ---- phase B state ----
+    int prev_e = -(1 << 29);      // end of the previous (kept) hot run
+    int run_start = -1;           // start of the hot run still open at the end of the previous queued word
+    const int ge_cap = tabs.ge_len - 1, brk_cap = tabs.brk_len - 1;
+    int t0 = 0;
     uint32_t starts = 0u, ends = 0u;
-    uint32_t m_next = K > 0 ? hp[0] : 0u, m_next2 = K > 1 ? hp[C] : 0u;     // the hot words two steps ahead are in flight
-    const uint32_t *hp_ahead = hp + 2 * C;                        // word k + 3 while the lane is at word k
     uint32_t pend_lab = 0u;       // labelled run that continues past the end of the season being closed
     int pend_s = 0, pend_e = 0;
 
-    // One iteration per season of this lane's table: consume (lane-asynchronously) every run that starts
-    // before the season ends, then close the season with the whole warp converged on the stores.
-    const int n_iter = max(n_north, n_south);                     // warp-uniform trip count; a lane whose table is shorter idles
-    for (int it = 0; it < n_iter; it++) {
+    // One iteration per season of the lanes' tables: consume every run that starts before the season ends, then close
+    // the season with the warp converged on the stores.
+    for (;;) {
         const bool open = ys < n_seasons;
+        if (!__any_sync(0xffffffffu, open)) break;
         bool done = !open;                                        // this lane has nothing more to do before the season closes
+        if (!open) qr = qw;                                       // a lane without seasons left drops what it has queued
         if (open && pend_lab) {
             const int days = min(pend_e, b_cur) - max(pend_s, a_cur);
             if (days > 0) account(pend_lab, (uint32_t)days);
             if (pend_e <= b_cur) pend_lab = 0u; else done = true;
         }
-        while (__any_sync(0xffffffffu, !done)) {
-            if (!done && ends != 0u) {
-                // ---- the next hot run [s, e) of the current word: leave it queued if it starts after this season ----
-                const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
-                if (s >= b_cur) done = true;
-                else {
-                    const int e = t0 + __ffs(ends) - 1;
-                    ends &= ends - 1;
-                    if (run_start >= 0) run_start = -1; else starts &= starts - 1;
-                    const int len = e - s, gap = s - prev_e;
-                    prev_e = e;
-
-                    // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
-                    const uint32_t ge = ge_s[min(len, ge_cap)];   // len >= min_duration
-                    inhw &= ~brk_s[min(gap, brk_cap)];            // B: the break before this run was too long
-                    const uint32_t A = ~inhw & ge;                // A: a new heatwave starts
-                    const uint32_t Cm = inhw & sublt;             // C: subsequent event of the current heatwave
-                    const uint32_t Dm = inhw & ~sublt;            // D: subsequent events used up
-                    const uint32_t Dn = Dm & ge;                  //    ... long enough: new heatwave id
-                    const uint32_t lab = A | Cm | Dn;
-                    fresh |= A | Dn;
-                    inhw = (inhw | A) & ~(Dm & ~ge);
-                    uint32_t borrow = Cm;
-                    sublt = 0u;
-#pragma unroll
-                    for (int q = 0; q < KS; q++) {                // rem -= 1 where C, rem = max_subs where D
-                        const uint32_t t = ~rem[q] & borrow;
-                        rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
-                        borrow = t;
-                        sublt |= rem[q];
+        for (;;) {
+            bool starved = false;
+            while (__any_sync(0xffffffffu, !done && !starved)) {
+                if (!done && !starved && ends == 0u) {
+                    // ---- the word is used up: take the next one from the queue ----
+                    if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }   // at most one start is left: the run stays open
+                    if (qr == qw) {
+                        if (k_ext > K) done = true;               // series exhausted
+                        else starved = true;
+                    } else {
+                        const uint32_t slot = (qr & (kScanQ - 1)) * 32;
+                        starts = q_st[slot]; ends = q_en[slot]; t0 = (int)q_t0[slot];
+                        qr++;
                     }
-                    const int days = min(e, b_cur) - max(s, a_cur);
-                    if (lab != 0u && days > 0) account(lab, (uint32_t)days);
-                    if (lab != 0u && e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; done = true; }
+                }
+                if (!done && !starved && ends != 0u) {
+                    // ---- the next hot run [s, e): leave it queued if it starts after this season ----
+                    const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
+                    if (s >= b_cur) done = true;
+                    else {
+                        const int e = t0 + __ffs(ends) - 1;
+                        ends &= ends - 1;
+                        if (run_start >= 0) run_start = -1; else starts &= starts - 1;
+                        const int len = e - s, gap = s - prev_e;
+                        prev_e = e;
+
+                        // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
+                        const uint32_t ge = ge_s[min(len, ge_cap)];   // len >= min_duration
+                        inhw &= ~brk_s[min(gap, brk_cap)];            // B: the break before this run was too long
+                        const uint32_t A = ~inhw & ge;                // A: a new heatwave starts
+                        const uint32_t Cm = inhw & sublt;             // C: subsequent event of the current heatwave
+                        const uint32_t Dm = inhw & ~sublt;            // D: subsequent events used up
+                        const uint32_t Dn = Dm & ge;                  //    ... long enough: new heatwave id
+                        const uint32_t lab = A | Cm | Dn;
+                        fresh |= A | Dn;
+                        inhw = (inhw | A) & ~(Dm & ~ge);
+                        uint32_t borrow = Cm;
+                        sublt = 0u;
+#pragma unroll
+                        for (int q = 0; q < KS; q++) {                // rem -= 1 where C, rem = max_subs where D
+                            const uint32_t t = ~rem[q] & borrow;
+                            rem[q] = ((rem[q] ^ borrow) & ~Dm) | (tabs.max_subs_plane[q] & Dm);
+                            borrow = t;
+                            sublt |= rem[q];
+                        }
+                        const int days = min(e, b_cur) - max(s, a_cur);
+                        if (lab != 0u && days > 0) account(lab, (uint32_t)days);
+                        if (lab != 0u && e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; done = true; }
+                    }
                 }
             }
-            if (!done && ends == 0u) {
-                // ---- the word is used up: on to the next one ----
-                if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }   // at most one start is left: the run stays open
-                k++;
-                if (k > K) done = true;                           // series exhausted
-                else {
-                    t0 = word_t0[k];
-                    const int nb = word_t0[k + 1] - t0;           // (1 for the virtual word K: a cold day closing a run at the series end)
-                    const uint32_t m = k < K ? m_next : 0u;
-                    m_next = m_next2;
-                    if (k + 2 < K) m_next2 = *hp_ahead;
-                    hp_ahead += C;
-                    const uint32_t prev = (m << 1) | (run_start >= 0 ? 1u : 0u);   // bit i = day i-1 hot
-                    starts = m & ~prev;
-                    ends = ~m & prev & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
-                }
-            }
+            if (!__any_sync(0xffffffffu, !done)) break;           // every lane has reached the end of its season
+            // some lane ran out of queued words: extract as many as fit the fullest queue (a word adds at most one entry)
+            const int room = kScanQ - (int)__reduce_max_sync(0xffffffffu, open ? qw - qr : 0u);
+            if (room == 0) break;                                 // blocked by a lane waiting for its next season: close those first
+            extract(min(room, K + 1 - k_ext), open);
         }
-        if (open) flush();
+        if (open && done) flush();
     }
 }
 
@@ -572,7 +648,13 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
         for (int i = 0; i < D; i++) if (h_defs[3 * i + 1] < g) lut[tabs.ge_len + g] |= 1u << i;
     if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice, st));
     const uint32_t *ge_tab = L.lut, *brk_tab = L.lut + tabs.ge_len;
-    const size_t scan_smem = (lut.size() + (size_t)K + 2) * sizeof(uint32_t);
+    // run filter (see k_scan): only when the look-back / look-ahead fits the 32-day neighbourhood
+    int min_min_dur = INT_MAX;
+    for (int i = 0; i < D; i++) min_min_dur = std::min(min_min_dur, h_defs[3 * i]);
+    tabs.f_lmin = min_min_dur;
+    tabs.f_bmax = max_break_all;
+    tabs.f_on = (min_min_dur >= 2 && min_min_dur <= 32 && max_break_all >= 0 && max_break_all <= 30 && g_scan_filter) ? 1 : 0;
+    const size_t scan_smem = ((size_t)kScanWarps * kScanQueueWords + lut.size() + (size_t)K + 3) * sizeof(uint32_t);
     if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~45 000 hot words (~4 000 years of daily data)
     const int64_t n_warps = ((C + 31) / 32) * P;                             // one warp per (32 cells, percentile)
     const unsigned scan_grid = (unsigned)((n_warps + kScanWarps - 1) / kScanWarps);
@@ -604,8 +686,7 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
         KernelTimer timer(kScan, st);
 #define HDP_LAUNCH_SCAN(NG, KS, BY)                                                                                      \
         do {                                                                                                             \
-            if (scan_smem > 48 * 1024)                                                                                   \
-                HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NG, KS, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NG, KS, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
             k_scan<NG, KS, BY><<<scan_grid, kScanWarps * 32, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, \
                                                                               sn, nn, ss, ns, Y, d_is_south, d_out);     \
         } while (0)
@@ -657,6 +738,8 @@ size_t hdp_b200_metrics_workspace_bytes(int64_t C, int64_t T, int64_t ld_t, int6
     const int64_t K = h_doy_map ? count_words(h_doy_map, T) : words_upper_bound(T, n_doy);
     return carve(nullptr, 0, C, T, ld_c != 1, K, n_doy, P, Y).total;
 }
+
+void hdp_b200_metrics_run_filter(int on) { g_scan_filter = on != 0; }
 
 int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                       const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,

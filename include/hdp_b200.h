@@ -114,6 +114,10 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
                      uint16_t *d_out,
                      void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Test hook: 0 makes k_scan feed every hot run to the definitions' state machines instead of first dropping the runs
+ * that cannot change any result (short runs after long breaks, see metric.cu); the outputs must be identical. */
+void hdp_b200_metrics_run_filter(int on);
+
 int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                           const double *h_thr, int n_doy, int P,
                           const int32_t *h_doy_map,

@@ -112,6 +112,16 @@ def test_thresholds_errors(core):
 
 
 # ------------------------------------------------------------------------------------------ path 2
+@pytest.fixture(params=["filter", "nofilter"], autouse=True)
+def scan_filter(request, core):
+    """Every test below runs twice: with k_scan's run filter (short runs after long breaks are dropped before the state
+    machines see them) and with every run fed through; both must match the reference bit for bit."""
+    from hdp_b200 import _lib
+    _lib.lib().hdp_b200_metrics_run_filter(1 if request.param == "filter" else 0)
+    yield request.param
+    _lib.lib().hdp_b200_metrics_run_filter(1)
+
+
 @pytest.mark.parametrize("name", ["noleap12", "std7", "noleap_mid5"])
 def test_metrics_golden(core, golden_metrics, name):
     g = golden_metrics

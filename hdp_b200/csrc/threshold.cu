@@ -433,6 +433,7 @@ constexpr int kSegNBF = kSegNB - 4;                               // finite buck
 constexpr int kSegRowsMax = 32;                                   // local rows 0 .. R of the prefix tables: R <= 31
 constexpr int kSegPst = 33, kSegCst = 34;                         // words per PB row, u16 per cum row (both odd in words)
 constexpr int kSegLongRun = 32;                                   // buckets with more samples are ordered by the whole warp
+constexpr int kSegCandTop = 8;                                   // largest per-row rank the candidate filter can ask for
 constexpr int kSegRanges = 5;                                     // <= 3 ranges of rows pooled (at least) once + <= 2 pooled twice
 // per-warp workspace (bytes)
 constexpr int kSegOffSv = 0;                                      // f32 [1024] the gathered tile row, then the sorted values
@@ -448,6 +449,8 @@ struct SegGeom {
     int S, n_seg;                       // days per segment, segments per cell
     int gc, n_groups;                   // cell groups (of kSegWarps cells) per L2-sized chunk, cell groups in all
     int ny_magic;                       // (k * ny_magic) >> 16 == k / n_y for k < 1024
+    int n_y;                            // samples per day-of-year row
+    int cand_m;                         // candidate filter: keep the samples >= min over rows of the row's cand_m-th largest; 0 = off
 };
 
 struct SelShared {                      // SelTable without the k_thr_ranked bookkeeping, in shared memory
@@ -713,26 +716,83 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     }
     __syncwarp();
 
+    // ---- 1b. candidate filter (high quantiles only) ----
+    // Every requested position is >= kmin, i.e. among the K = n - kmin largest samples of its window.  A window pools W
+    // rows; with m = ceil(K / W) and tau = min over the segment's rows of the row's m-th largest sample, every window holds
+    // at least m W >= K samples >= tau, so its K largest are all >= tau: only those "candidates" need to be ordered.
+    // The window's other members are all smaller than the sample at position kmin, so position pos of the window is
+    // position pos - (n - candidates in the window) among its candidates (phase 6).
+    int NEc = NE;                                                 // samples that take part in the ordering
+    uint32_t rw4[kSegRounds / 4];                                 // local rows of this lane's candidates, four per register
+    const bool cand = geo.cand_m > 0 && !nonfinite;               // warp-uniform
+    if (cand) {
+        const int R0 = (NE * geo.ny_magic) >> 16;
+        float t[kSegCandTop];
+#pragma unroll
+        for (int i = 0; i < kSegCandTop; i++) t[i] = -pinf;
+        if (lane < R0) {                                          // lane = row: the row's largest samples, descending
+            const uint32_t a0 = s_sv + 4u * (uint32_t)(lane * geo.n_y);
+            for (int y = 0; y < geo.n_y; y++) {
+                float v = lds_f32(a0 + 4u * y);
+#pragma unroll
+                for (int i = 0; i < kSegCandTop; i++) { const float hi = fmaxf(t[i], v); v = fminf(t[i], v); t[i] = hi; }
+            }
+        }
+        float tau = pinf;
+#pragma unroll
+        for (int i = 0; i < kSegCandTop; i++) if (i == geo.cand_m - 1 && lane < R0) tau = t[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+        __syncwarp();                                             // the tile has been read: its place takes the compacted candidates
+        int base = 0;
+#pragma unroll
+        for (int m = 0; m < kSegRounds; m++) {
+            if (32 * m < NE) {                                    // warp-uniform
+                const bool keep = NE - lane > 32 * m && x[m] >= tau;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const uint32_t pos = (uint32_t)(base + __popc(bal & ((1u << lane) - 1u)));
+                    sts_f32(s_sv + 4u * pos, x[m]);
+                    sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
+                }
+                base += __popc(bal);
+            }
+        }
+        __syncwarp();
+        NEc = base;
+#pragma unroll
+        for (int m = 0; m < kSegRounds; m++) {
+            if ((m & 3) == 0) rw4[m >> 2] = 0u;
+            if (32 * m < NEc) {                                   // warp-uniform
+                const bool have = NEc - lane > 32 * m;
+                x[m] = have ? lds_f32(s_sv + 4u * (32 * m + lane)) : 0.0f;
+                rw4[m >> 2] |= (have ? lds_u8(s_rw + 32 * m + lane) : 0u) << (8 * (m & 3));
+            }
+        }
+        vmin = tau;
+        __syncwarp();
+    }
+
     // ---- 2. monotone buckets; one atomic claims the slot inside the bucket ----
     const float range = vmax - vmin;
     const float scale = (range > 0.0f && range < pinf) ? (float)(kSegNBF - 1) / range : 0.0f;
     uint32_t pk[kSegRounds];                                      // where the counter is | slot
     int n_wl = 0;                                                 // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int nl = NE - lane;                                     // round m holds a sample of this lane iff nl > 32 m
+    const int nl = NEc - lane;                                     // round m holds a sample of this lane iff nl > 32 m
     if (!nonfinite) {
 #pragma unroll
         for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
 #pragma unroll
             for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
-            if (32 * m0 < NE) seg_claim<false>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
+            if (32 * m0 < NEc) seg_claim<false>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
         }
     } else {
 #pragma unroll
         for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
 #pragma unroll
             for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
-            if (32 * m0 < NE) seg_claim<true>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
+            if (32 * m0 < NEc) seg_claim<true>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
         }
     }
     __syncwarp();
@@ -760,7 +820,7 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     // ---- 4. scatter (value, local row) to the sorted position; exact order inside the work-list buckets ----
 #pragma unroll
     for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
-        if (32 * m0 < NE) {                                       // warp-uniform
+        if (32 * m0 < NEc) {                                       // warp-uniform
             uint32_t bw[kSegBatch];
 #pragma unroll
             for (int j = 0; j < kSegBatch; j++) bw[j] = lds_u32(s_cnt + ((pk[m0 + j] >> 9) & ~3u));   // the batch's base lookups overlap
@@ -769,7 +829,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
                 if (nl > 32 * (m0 + j)) {
                     const uint32_t pos = ((bw[j] >> ((pk[m0 + j] >> 6) & 16u)) & 0xffffu) + (pk[m0 + j] & 1023u);
                     sts_f32(s_sv + 4u * pos, x[m0 + j]);
-                    sts_u8(s_rw + pos, ((uint32_t)(32 * (m0 + j) + lane) * (uint32_t)geo.ny_magic) >> 16);
+                    const uint32_t row_all = ((uint32_t)(32 * (m0 + j) + lane) * (uint32_t)geo.ny_magic) >> 16;
+                    sts_u8(s_rw + pos, cand ? (rw4[(m0 + j) >> 2] >> (8 * ((m0 + j) & 3))) & 0xffu : row_all);
                 }
             }
         }
@@ -848,7 +909,7 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     __syncwarp();
 #pragma unroll
     for (int m0 = 0; m0 < kSegRounds; m0 += kSegBatch) {
-        if (32 * m0 < NE) {                                       // warp-uniform
+        if (32 * m0 < NEc) {                                       // warp-uniform
             uint32_t rr[kSegBatch];
 #pragma unroll
             for (int j = 0; j < kSegBatch; j++) rr[j] = lds_u8(s_rw + 32 * (m0 + j) + lane);
@@ -875,6 +936,7 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
             sts_u16(s_cum + 2u * (lane * kSegCst + w), run);
             run += __popc(lds_u32(s_pb + 4u * (lane * kSegPst + w)));
         }
+        sts_u16(s_cum + 2u * (lane * kSegCst + 32), run);          // all of them
     }
     __syncwarp();
 
@@ -899,7 +961,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
             win.ca[0] = cum_p + r1 * kSegCst; win.cb[0] = cum_p + r0 * kSegCst;
             win.pa[0] = pb_p + r1 * kSegPst; win.pb[0] = pb_p + r0 * kSegPst;
             win.n1 = 1; win.nr = 1;
-            seg_pick<1>(win, pos_lo, pos_hi, lr_lo, lr_hi);
+            const int off = cand ? n - win.before(32) : 0;        // the window's members below tau
+            seg_pick<1>(win, pos_lo - off, pos_hi - off, lr_lo, lr_hi);
             if (nonfinite) {
                 const int b_pinf = seg_below<1>(win, L_pinf, n);
                 w_ninf = seg_below<1>(win, L_ninf, n);
@@ -920,7 +983,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
                 win.ca[k] = cum_p + r1 * kSegCst; win.cb[k] = cum_p + r0 * kSegCst;
                 win.pa[k] = pb_p + r1 * kSegPst; win.pb[k] = pb_p + r0 * kSegPst;
             }
-            seg_pick<kSegRanges>(win, pos_lo, pos_hi, lr_lo, lr_hi);
+            const int off = cand ? n - win.before(32) : 0;
+            seg_pick<kSegRanges>(win, pos_lo - off, pos_hi - off, lr_lo, lr_hi);
             if (nonfinite) {
                 const int b_pinf = seg_below<kSegRanges>(win, L_pinf, n);
                 w_ninf = seg_below<kSegRanges>(win, L_ninf, n);
@@ -963,7 +1027,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         wb.ca[0] = cum_p + r1b * kSegCst; wb.cb[0] = cum_p + r0b * kSegCst; wb.pa[0] = pb_p + r1b * kSegPst; wb.pb[0] = pb_p + r0b * kSegPst;
         wa.n1 = wa.nr = wb.n1 = wb.nr = 1;
         int la, ha, lb, hb;
-        seg_pick2(wa, wb, lo_a, hi_a, lo_b, hi_b, la, ha, lb, hb);
+        const int off_a = cand ? n - wa.before(32) : 0, off_b = cand ? n - wb.before(32) : 0;
+        seg_pick2(wa, wb, lo_a - off_a, hi_a - off_a, lo_b - off_b, hi_b - off_b, la, ha, lb, hb);
         out_c[(d0 + dl_a) * P + p_a] = __dadd_rn(__dmul_rn((double)sv_p[la], s_sel.w_lo[p_a]), __dmul_rn((double)sv_p[ha], s_sel.w_hi[p_a]));
         out_c[(d0 + dl_b) * P + p_b] = __dadd_rn(__dmul_rn((double)sv_p[lb], s_sel.w_lo[p_b]), __dmul_rn((double)sv_p[hb], s_sel.w_hi[p_b]));
         return true;
@@ -1159,6 +1224,8 @@ static void plan_seg(const int32_t *time_index, const int32_t *win_rows, int64_t
         if (2 * S < W - 1) return;                                          // more than 3x halo: k_thr_ranked does better
         if (!plan_seg_try(time_index, win_rows, T_b, n_doy, n_y, W, S, sp)) continue;
         sp.geo.ny_magic = magic;
+        sp.geo.n_y = n_y;
+        sp.geo.cand_m = 0;
         sp.usable = true;
         return;
     }
@@ -1206,6 +1273,7 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
 
 static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
 static int g_force_ranked = 0;
+static int g_seg_candidates = 1;     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
 
 // The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
 // capacity so that every chunk sees the tables at the same place) and `tables_resident` skips the table uploads when
@@ -1280,6 +1348,13 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
             attr_done = true;
         }
         SegGeom geo = seg.geo;
+        {
+            // candidate filter (k_thr_seg phase 1b): every requested position is among the K largest of its window
+            int kmin = (int)b - 1;
+            for (int p = 0; p < P; p++) kmin = std::min(kmin, sel.pos_lo[p]);
+            const int K_top = (int)b - kmin, m = (K_top + W - 1) / W;
+            geo.cand_m = (g_seg_candidates && m <= kSegCandTop && 3 * m <= n_y) ? m : 0;      // worth it for the top third only
+        }
         geo.n_groups = (int)((C + kSegWarps - 1) / kSegWarps);
         geo.gc = std::min(thr_chunk_groups(T_b), geo.n_groups);
         const int64_t n_chunks = (geo.n_groups + geo.gc - 1) / geo.gc;
@@ -1327,7 +1402,7 @@ using namespace hdp;
 
 extern "C" {
 
-void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; }
+void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                                            int n_doy, int n_y, int W, int P)

@@ -78,8 +78,9 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
                         double *d_out,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
-/* Test hook: route every hdp_b200_thresholds call through the generic gather+sort kernel (the path used for
- * tables the ranked kernel does not cover: rows pooled more than twice, windows that do not fit shared memory). */
+/* Test hook: which kernel hdp_b200_thresholds uses.  0 = default (k_thr_seg with its candidate filter where the tables
+ * allow, else k_thr_ranked, else k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled
+ * any number of times); 2 = k_thr_ranked instead of k_thr_seg; 3 = k_thr_seg without the candidate filter. */
 void hdp_b200_thresholds_force_generic(int on);
 
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,

@@ -32,12 +32,12 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
-@pytest.fixture(params=["seg", "ranked", "generic"])
+@pytest.fixture(params=["seg", "seg_all", "ranked", "generic"])
 def thr_path(request, core):
-    """All three threshold paths: the fast pair (k_thr_order + k_thr_segsel, which hands badly conditioned cells to
-    k_thr_ranked), k_thr_ranked for every cell, and the generic gather+sort fallback."""
+    """Every threshold path: k_thr_seg with and without its candidate filter, k_thr_ranked, and the generic gather+sort
+    fallback."""
     from hdp_b200 import _lib
-    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2}[request.param])
+    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2, "seg_all": 3}[request.param])
     yield request.param
     _lib.lib().hdp_b200_thresholds_force_generic(0)
 
@@ -96,6 +96,37 @@ def test_thresholds_many_percentiles_and_leap(core, thr_path):
     q = np.linspace(0.80, 0.99, 20)
     want = oracle.thresholds_batch(x, wt.window_samples(), q)
     assert bits_equal(core.thresholds_array(dev(x), wt, q).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("calendar,years,radius,q", [
+    ("noleap", 30, 7, np.arange(0.9, 1.0, 0.01)),                      # the README sweep: 4 candidates per row
+    ("noleap", 12, 7, np.array([0.75, 0.9, 0.999, 1.0])),              # the filter's loosest setting / the maximum
+    ("standard", 9, 15, np.linspace(0.85, 0.99, 15)),                  # leap rows with -1 pads, 31-day window
+    ("360_day", 20, 2, np.array([0.95, 0.97])),
+])
+def test_thresholds_high_quantiles_candidate_filter(core, thr_path, calendar, years, radius, q):
+    # high quantiles only: k_thr_seg orders just the samples above a per-segment bound (candidate filter); ties at the
+    # bound, constant series, outliers, steps and trends must not change a single bit
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(29)
+    ax = tb.TimeAxis.date_range("1961-01-01", f"{1960 + years}-12-30" if calendar == "360_day" else f"{1960 + years}-12-31", calendar)
+    wt = tb.window_tables(ax.dayofyr, radius)
+    T, C = len(ax), 67
+    doy = ax.dayofyr[:, None]
+    x = (15 + 12 * np.sin(2 * np.pi * (doy - 110) / 365) + 3 * rng.standard_normal((T, C))).astype(np.float32)
+    x[:, 0] = np.round(x[:, 0])                               # heavy ties
+    x[:, 1] = 2.5                                             # constant
+    x[:, 2] = np.where(rng.random(T) < 0.5, 1.0, 2.0)         # two values
+    x[:, 3] = np.arange(T, dtype=np.float32) * np.float32(1e-3)   # a trend: the last year holds every window's top
+    x[:, 4] = -np.arange(T, dtype=np.float32)
+    x[T // 2, 5] = 1e30                                       # one outlier squeezes the candidates into one bucket
+    x[:, 6] = np.where(rng.random(T) < 0.9, -5.0, x[:, 6])    # 90 % fill value below the data
+    x[:, 7] = np.where(rng.random(T) < 0.3, 99.0, x[:, 7])    # 30 % fill value above the data: ties inside the top
+    x[:, 8] = (np.arange(T) % 7).astype(np.float32)
+    x[:, 9] = np.float32(20.0) + np.arange(T, dtype=np.float32) * np.float32(2e-6)
+    want = oracle.thresholds_batch(x, wt.window_samples(), q)
+    got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
+    assert bits_equal(got, want)
 
 
 def test_thresholds_errors(core):

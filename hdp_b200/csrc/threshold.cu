@@ -625,6 +625,22 @@ __device__ __forceinline__ void seg_claim(const float *x, uint32_t *pk, int m0, 
     }
 }
 
+// the M-th largest of the n_y samples at shared address a0
+template <int M>
+__device__ __forceinline__ float seg_row_top(uint32_t a0, int n_y)
+{
+    float t[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) t[i] = -__int_as_float(0x7f800000);
+#pragma unroll 2
+    for (int y = 0; y < n_y; y++) {
+        float v = lds_f32(a0 + 4u * y);
+#pragma unroll
+        for (int i = 0; i < M; i++) { const float hi = fmaxf(t[i], v); v = fminf(t[i], v); t[i] = hi; }
+    }
+    return t[M - 1];
+}
+
 __global__ void __launch_bounds__(kSegWarps * 32, 2)
 k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
           const int *__restrict__ seg_time, const int *__restrict__ seg_ne, const uint4 *__restrict__ doy_rng,
@@ -727,39 +743,43 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     const bool cand = geo.cand_m > 0 && !nonfinite;               // warp-uniform
     if (cand) {
         const int R0 = (NE * geo.ny_magic) >> 16;
-        float t[kSegCandTop];
-#pragma unroll
-        for (int i = 0; i < kSegCandTop; i++) t[i] = -pinf;
-        if (lane < R0) {                                          // lane = row: the row's largest samples, descending
+        float tau = pinf;                                         // lane = row: the row's cand_m-th largest sample
+        if (lane < R0) {
             const uint32_t a0 = s_sv + 4u * (uint32_t)(lane * geo.n_y);
-            for (int y = 0; y < geo.n_y; y++) {
-                float v = lds_f32(a0 + 4u * y);
-#pragma unroll
-                for (int i = 0; i < kSegCandTop; i++) { const float hi = fmaxf(t[i], v); v = fminf(t[i], v); t[i] = hi; }
+            switch (geo.cand_m) {                                 // warp-uniform
+            case 1: tau = seg_row_top<1>(a0, geo.n_y); break;
+            case 2: tau = seg_row_top<2>(a0, geo.n_y); break;
+            case 3: tau = seg_row_top<3>(a0, geo.n_y); break;
+            case 4: tau = seg_row_top<4>(a0, geo.n_y); break;
+            case 5: tau = seg_row_top<5>(a0, geo.n_y); break;
+            case 6: tau = seg_row_top<6>(a0, geo.n_y); break;
+            case 7: tau = seg_row_top<7>(a0, geo.n_y); break;
+            default: tau = seg_row_top<8>(a0, geo.n_y); break;
             }
         }
-        float tau = pinf;
-#pragma unroll
-        for (int i = 0; i < kSegCandTop; i++) if (i == geo.cand_m - 1 && lane < R0) tau = t[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+        // every lane packs its own candidates behind those of the lanes before it (the order does not matter)
+        int mine = 0;
+#pragma unroll
+        for (int m = 0; m < kSegRounds; m++) mine += (NE - lane > 32 * m && x[m] >= tau) ? 1 : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        NEc = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();                                             // the tile has been read: its place takes the compacted candidates
-        int base = 0;
+        uint32_t pos = (uint32_t)(incl - mine);
 #pragma unroll
         for (int m = 0; m < kSegRounds; m++) {
             if (32 * m < NE) {                                    // warp-uniform
-                const bool keep = NE - lane > 32 * m && x[m] >= tau;
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const uint32_t pos = (uint32_t)(base + __popc(bal & ((1u << lane) - 1u)));
+                if (NE - lane > 32 * m && x[m] >= tau) {
                     sts_f32(s_sv + 4u * pos, x[m]);
                     sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
+                    pos++;
                 }
-                base += __popc(bal);
             }
         }
         __syncwarp();
-        NEc = base;
 #pragma unroll
         for (int m = 0; m < kSegRounds; m++) {
             if ((m & 3) == 0) rw4[m >> 2] = 0u;

@@ -50,6 +50,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(label: str, cells: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel(s) in `label`, from the committed ncu
+    `--set full` capture of this round (profiles/traffic.json, written by tools/ncu_summary.py), scaled to `cells`."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        k = json.load(f)["kernels"]
+    total = 0.0
+    for name in label.split("+"):
+        if name not in k:
+            return None
+        total += k[name]["dram_bytes"] * cells / k[name]["cells"]
+    return total
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -291,7 +307,7 @@ def main():
             label = "+".join(k for k in thr_kernels if k in kernel_ms)
         achieved = alg_bytes[dominant] / (dur / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": label, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dominant],
+                    "traffic": measured_traffic(label, C), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dominant],
                     "kernel_ms": kernel_ms, "kernel_share": kernel_share, "kernel_launches_per_measure": kernel_launches,
                     "unit_of_launch": "all launches of the kernel for one measure (64 800 cells)"}
     # whole-step roofline: all algorithmic bytes of the step over the step time

@@ -114,6 +114,15 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU legs (oracle port): cpu_baseline of our arm and the whole of --impl reference
 # --------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use every
+    host core, so they ask the oracle for this many threads explicitly instead of relying on the OpenMP default."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_tables(wl):
     from hdp_b200 import _tables as tb
     wt = wl.window_tables()
@@ -121,10 +130,11 @@ def cpu_tables(wl):
     return wt, tb.doy_map(wl.run_axis().dayofyr), st
 
 
-def cpu_pass(wl, base, run, is_south, threads=0):
+def cpu_pass(wl, base, run, is_south, threads=None):
     """One pass of the reference algorithm (oracle port, OpenMP over cells) on [T, n] host arrays.
     Returns (seconds thresholds, seconds metrics, thresholds, metrics)."""
     import oracle
+    threads = threads or host_cores()
     wt, dm, st = cpu_tables(wl)
     win = wt.window_samples()
     t0 = time.perf_counter()
@@ -146,7 +156,7 @@ def run_reference(args):
     import oracle
     from hdp_b200 import workloads, synth
     wl = workloads.get(args.workload)
-    cores = oracle.max_threads()
+    cores = host_cores()
     lat, _ = synth.grid_latitudes(wl.n_lat, wl.n_lon)
     n = args.cells or max(8 * cores, 64)
     sel = np.linspace(0, wl.cells - 1, n).astype(np.int64)
@@ -368,8 +378,7 @@ def main():
 
     # ---- cpu_baseline: oracle port on a bounded sample of measure 0, all host cores, rank 0 only; also a parity check
     if rank == 0 and not args.no_cpu:
-        import oracle
-        cores = oracle.max_threads()
+        cores = host_cores()
         n_probe = min(C, max(cores, 8))
         sel = np.linspace(0, C - 1, n_probe).astype(np.int64)
         sel_t = torch.as_tensor(sel, device=dev)

@@ -199,11 +199,25 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     uint32_t *queues = smem_scan;                                 // [warps][3][kScanQ][32]
     uint32_t *ge_s = queues + kScanWarps * kScanQueueWords;       // [ge_len]  definitions with min_dur <= len
     uint32_t *brk_s = ge_s + tabs.ge_len;                         // [brk_len] definitions with max_break < gap
-    int *word_t0 = (int *)(brk_s + tabs.brk_len);                 // [K + 3] first day of every hot word; word K is a virtual cold day at T
+    // [K + 1] per hot word {first day, days, unknown days of the NEXT word (they count as hot), unknown days after that};
+    // word K is a virtual cold day at T that closes a run still open at the end of the series
+    int4 *word_meta = (int4 *)(smem_scan + ((kScanWarps * kScanQueueWords + tabs.ge_len + tabs.brk_len + 3) & ~3));
     const int tid = threadIdx.x, nthreads = kScanWarps * 32;
     for (int i = tid; i < tabs.ge_len; i += nthreads) ge_s[i] = ge_tab[i];
     for (int i = tid; i < tabs.brk_len; i += nthreads) brk_s[i] = brk_tab[i];
-    for (int i = tid; i <= K + 2; i += nthreads) word_t0[i] = i < K ? words[i].x : T + (i - K);
+    for (int i = tid; i <= K; i += nthreads) {
+        int4 m = make_int4(T, 1, 0, 0);
+        if (i < K) {
+            const int4 w = words[i];
+            m.x = w.x; m.y = w.y;
+            if (i + 1 < K) {                                      // days past the end of the series are known: cold
+                const int nb1 = words[i + 1].y;
+                m.z = nb1 == 32 ? 0 : (int)(0xffffffffu << nb1);
+                m.w = w.y == 32 ? 0 : (int)(0xffffffffu << w.y);
+            }
+        }
+        word_meta[i] = m;
+    }
     __syncthreads();
 
     // warp -> (group of 32 cells, percentile): every warp of the grid has work
@@ -280,6 +294,7 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     int k_ext = 0;                                                // next word to extract (warp-uniform); word K is the virtual one
     uint32_t w0 = K > 0 ? hp[0] : 0u, w1 = K > 1 ? hp[C] : 0u, w2 = K > 2 ? hp[2 * C] : 0u, w3 = K > 3 ? hp[3 * C] : 0u;
     const uint32_t *hp_ahead = hp + 4 * C;                        // word k_ext + 4
+    const int64_t pf_off = (int64_t)kScanQ * C;
     uint32_t tail = 0u, a_tail = 0u;                              // hot days / `long` seeds of the 32 days before word k_ext (bit 31 = yesterday)
     uint32_t carry_keep = 0u, open_f = 0u;                        // a kept `near` run / any kept run reaches the end of the previous word
     uint32_t qr = 0u, qw = 0u;                                    // ring buffer read / write counters
@@ -288,34 +303,38 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
 
     auto extract = [&](int n_words, bool live) {
         for (int i = 0; i < n_words; i++) {
-            const int k = k_ext;
-            const int t0 = word_t0[k], nb = word_t0[k + 1] - t0;   // (1 for the virtual word K: a cold day closing a run at the series end)
-            const uint32_t cur = k < K ? w0 : 0u;
-            const uint32_t vmask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            const int4 wm = word_meta[k_ext];                     // warp-uniform
+            const int t0 = wm.x, nb = wm.y;
+            const uint32_t cur = w0;
+            const uint32_t vmask = 0xffffffffu >> (32 - nb);
             uint32_t keep = cur;
             if (f_on) {
-                // E = the 64 days starting at this word (lo, hi): the next word follows at bit nb; days that are not
-                // known yet count as hot, days past the end of the series are cold
-                const bool last = k + 1 >= K;
-                const int nb1 = word_t0[k + 2] - word_t0[k + 1];
-                const uint32_t fut = last ? 0u : (w1 | (nb1 == 32 ? 0u : 0xffffffffu << nb1));
+                // E = the 64 days starting at this word (lo, hi): the next word follows at bit nb
+                const uint32_t fut = w1 | (uint32_t)wm.z;
                 uint32_t lo = cur, hi = fut;
                 if (nb < 32) {                                     // warp-uniform
                     lo = cur | (fut << nb);
-                    hi = (fut >> (32 - nb)) | (last ? 0u : 0xffffffffu << nb);
+                    hi = (fut >> (32 - nb)) | (uint32_t)wm.w;
                 }
-                uint32_t a = lo;                                   // a_j: days j .. j + lmin - 1 are all hot
-                for (int j = 1; j < f_lmin; j++) a &= __funnelshift_r(lo, hi, j);
+                // a_j: days j .. j + lmin - 1 are all hot;  b_j: day j belongs to lmin consecutive hot days
+                // near_j: one of the days j - 2 .. j - bmax - 1 is hot
+                uint32_t a = lo, near = 0u;
+#pragma unroll
+                for (int j = 1; j < 4; j++) if (j < f_lmin) a &= __funnelshift_r(lo, hi, j);
+                for (int j = 4; j < f_lmin; j++) a &= __funnelshift_r(lo, hi, j);
                 a &= vmask;
-                uint32_t b = a;                                    // b_j: day j belongs to lmin consecutive hot days
-                for (int j = 1; j < f_lmin; j++) b |= __funnelshift_l(a_tail, a, j);
-                uint32_t near = 0u;                                // near_j: one of the days j - 2 .. j - bmax - 1 is hot
-                for (int j = 2; j <= f_bmax + 1; j++) near |= __funnelshift_l(tail, cur, j);
+                uint32_t b = a;
+#pragma unroll
+                for (int j = 1; j < 4; j++) if (j < f_lmin) b |= __funnelshift_l(a_tail, a, j);
+                for (int j = 4; j < f_lmin; j++) b |= __funnelshift_l(a_tail, a, j);
+#pragma unroll
+                for (int j = 2; j < 5; j++) if (j <= f_bmax + 1) near |= __funnelshift_l(tail, cur, j);
+                for (int j = 5; j <= f_bmax + 1; j++) near |= __funnelshift_l(tail, cur, j);
                 const uint32_t prev = __funnelshift_l(tail, cur, 1);                   // day j - 1 is hot
                 const uint32_t ns = (cur & ~prev & near) | (carry_keep & cur & 1u);
                 const uint32_t fill = ((cur + ns) ^ cur) & cur;    // the whole run above every kept run start
                 keep = (b | fill) & cur;
-                carry_keep = (fill >> (nb - 1)) & 1u;
+                carry_keep = fill >> (nb - 1);                     // (bit 0 is what is used)
                 tail = nb == 32 ? cur : __funnelshift_r(tail, cur, nb);
                 a_tail = nb == 32 ? a : __funnelshift_r(a_tail, a, nb);
             }
@@ -328,8 +347,8 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                 qw++;
             }
             w0 = w1; w1 = w2; w2 = w3;
-            if (k + 4 < K) w3 = *hp_ahead;
-            if (k + 4 + kScanQ < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp_ahead + (int64_t)kScanQ * C));   // the next burst's words
+            w3 = k_ext + 4 < K ? __ldg(hp_ahead) : 0u;            // (words past the end read as cold)
+            if (k_ext + 4 + kScanQ < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp_ahead + pf_off));   // the next burst's words
             hp_ahead += C;
             k_ext++;
         }
@@ -654,8 +673,8 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
     tabs.f_lmin = min_min_dur;
     tabs.f_bmax = max_break_all;
     tabs.f_on = (min_min_dur >= 2 && min_min_dur <= 32 && max_break_all >= 0 && max_break_all <= 30 && g_scan_filter) ? 1 : 0;
-    const size_t scan_smem = ((size_t)kScanWarps * kScanQueueWords + lut.size() + (size_t)K + 3) * sizeof(uint32_t);
-    if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~45 000 hot words (~4 000 years of daily data)
+    const size_t scan_smem = (((size_t)kScanWarps * kScanQueueWords + lut.size() + 3) & ~(size_t)3) * sizeof(uint32_t) + ((size_t)K + 1) * sizeof(int4);
+    if (scan_smem > 200 * 1024) return HDP_B200_ERR_UNSUPPORTED;             // > ~9 000 hot words (~800 years of daily data)
     const int64_t n_warps = ((C + 31) / 32) * P;                             // one warp per (32 cells, percentile)
     const unsigned scan_grid = (unsigned)((n_warps + kScanWarps - 1) / kScanWarps);
     // accumulators: four definitions per register when every season fits 8-bit lanes, else two

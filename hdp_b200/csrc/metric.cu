@@ -33,6 +33,7 @@ namespace hdp {
 constexpr int kTileCells = 32;
 constexpr int kTileDoy = 32;
 constexpr int kHotYears = 2;  // words (years) a warp compares against one register copy of the day's thresholds
+constexpr int kFillLoads = 5;  // doubles of the threshold tile a lane has in flight
 constexpr int kHotDays = 16;  // days of each of them whose samples are in flight together
 constexpr int kTilePad = 33;   // [.. ][33]: conflict-free both for the e-major fill and the lane-major reads
 
@@ -77,17 +78,32 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
     const int64_t c0 = (int64_t)blockIdx.x * kTileCells;
     const int Ppad = (P + PG - 1) / PG * PG;
     const int nd = min(kTileDoy, n_doy - db * kTileDoy);
-    const int per_cell = kTileDoy * Ppad;
 
-    // Threshold tile: per cell the (doy, percentile) block is contiguous in the reference's [C, n_doy, P] order.
-    for (int idx = tid; idx < kTileCells * per_cell; idx += 256) {
-        int cell = idx / per_cell, e = idx - cell * per_cell;
-        int j = e / Ppad, p = e - j * Ppad;
-        float v = __int_as_float(0x7f800000);             // +inf: never exceeded (padding percentiles / days)
-        if (c0 + cell < C && j < nd && p < P)
-            v = __double2float_rd(thr[((c0 + cell) * n_doy + (db * kTileDoy + j)) * (int64_t)P + p]);
-        const int g = p / PG, q = p - g * PG;
-        thr_s[((g * kTileDoy + j) * PG + q) * kTilePad + cell] = v;
+    // Threshold tile.  Per cell the (doy, percentile) block of this tile is nd * P contiguous doubles in the reference's
+    // [C, n_doy, P] order: a warp reads them with consecutive lanes, kFillLoads independent loads per lane in flight
+    // (the fill is pure HBM latency), and scatters them to [group][doy][PG][cell].  Padding percentiles / days: +inf.
+    const int n_el = nd * P;                               // doubles per cell
+    if (nd < kTileDoy || Ppad != P)
+        for (int i = tid; i < (Ppad / PG) * kTileDoy * PG * kTilePad; i += 256) thr_s[i] = __int_as_float(0x7f800000);
+    __syncthreads();
+    for (int e0 = 0; e0 < n_el; e0 += 32 * kFillLoads) {
+        int dst[kFillLoads];
+#pragma unroll
+        for (int i = 0; i < kFillLoads; i++) {
+            const int e = e0 + 32 * i + lane;
+            const int j = e / P, p = e - j * P, g = p / PG, q = p - g * PG;
+            dst[i] = e < n_el ? ((g * kTileDoy + j) * PG + q) * kTilePad : -1;
+        }
+        for (int cell = warp; cell < kTileCells; cell += 8) {
+            if (c0 + cell >= C) break;
+            const double *src = thr + ((c0 + cell) * n_doy + (int64_t)db * kTileDoy) * P + e0 + lane;
+            double v[kFillLoads];
+#pragma unroll
+            for (int i = 0; i < kFillLoads; i++) v[i] = dst[i] >= 0 ? __ldg(src + 32 * i) : 0.0;
+#pragma unroll
+            for (int i = 0; i < kFillLoads; i++)
+                if (dst[i] >= 0) thr_s[dst[i] + cell] = __double2float_rd(v[i]);
+        }
     }
     __syncthreads();
 

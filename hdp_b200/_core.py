@@ -173,6 +173,59 @@ def hot_days_array(measure, thresholds, doy_map):
 
 
 # ----------------------------------------------------------------------------------------------
+# hdp.measure's elementwise pre-pass on the device (reference hdp/measure.py:10-94, 183-194)
+# ----------------------------------------------------------------------------------------------
+
+def _f32_dense(x, name: str):
+    torch = _torch()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous float32 CUDA tensor")
+    return x
+
+
+def _measure_call(fn_name: str, temp, rh, flag, out):
+    torch = _torch()
+    temp = _f32_dense(temp, "temp")
+    if rh is not None:
+        rh = _f32_dense(rh, "rh")
+        if rh.shape != temp.shape:
+            raise ValueError("temp and rh must have the same shape")
+    out = torch.empty_like(temp) if out is None else _f32_dense(out, "out")
+    if out.shape != temp.shape:
+        raise ValueError("out must have the shape of temp")
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device(temp.device):
+        if fn_name == "hdp_b200_heat_index":
+            rc = L.hdp_b200_heat_index(temp.data_ptr(), rh.data_ptr(), temp.numel(), out.data_ptr(), stream)
+        elif fn_name == "hdp_b200_heat_index_measure":
+            rc = L.hdp_b200_heat_index_measure(temp.data_ptr(), rh.data_ptr(), temp.numel(), int(flag), out.data_ptr(), stream)
+        else:
+            rc = L.hdp_b200_to_celsius(temp.data_ptr(), temp.numel(), int(flag), out.data_ptr(), stream)
+    _lib.check(rc, fn_name)
+    return out
+
+
+def heat_index_array(temp_f, rh_pct, out=None):
+    """``heat_index`` ufunc (reference hdp/measure.py:61-94): degF and % in, degF out, float32, bit-identical."""
+    return _measure_call("hdp_b200_heat_index", temp_f, rh_pct, 0, out)
+
+
+def heat_index_measure_array(temp_c, rh, rh_is_fraction: bool = False, out=None):
+    """The ``{name}_hi`` measure of ``format_standard_measures`` (reference hdp/measure.py:183-194) in one pass:
+    degC -> degF, heat index against rh (% or g/g), degF -> degC."""
+    return _measure_call("hdp_b200_heat_index_measure", temp_c, rh, 1 if rh_is_fraction else 0, out)
+
+
+TEMPERATURE_UNIT_CODES = {"degC": 0, "C": 0, "degK": 1, "K": 1, "degF": 2, "F": 2}
+
+
+def to_celsius_array(temp, units: str, out=None):
+    """``convert_temp_units`` (reference hdp/measure.py:10-41, 136-149) in float32, like the reference's array arithmetic."""
+    return _measure_call("hdp_b200_to_celsius", temp, None, TEMPERATURE_UNIT_CODES[units], out)
+
+
+# ----------------------------------------------------------------------------------------------
 # host-buffer variants (NumPy in, NumPy out; the library pipelines H2D / kernels / D2H over cell chunks)
 # ----------------------------------------------------------------------------------------------
 
@@ -239,7 +292,7 @@ def launch_count() -> int:
 
 
 KERNEL_NAMES = {1: "normalize", 2: "k_thr_generic", 3: "k_hot_words", 4: "k_scan", 5: "k_unpack_mask",
-                6: "k_thr_seg", 7: "k_thr_ranked"}
+                6: "k_thr_seg", 7: "k_thr_ranked", 8: "k_measure"}
 
 
 def timing_enable(on: bool) -> None:

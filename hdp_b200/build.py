@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libhdp_b200.so")
-SOURCES = ["abi.cu", "threshold.cu", "metric.cu", "host.cu"]
+SOURCES = ["abi.cu", "threshold.cu", "metric.cu", "measure.cu", "host.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -139,6 +139,20 @@ int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t
                       uint8_t *d_mask,
                       void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Elementwise pre-pass of hdp.measure on the device ("next" row of the scope table; format_standard_measures itself
+ * stays host Python).   reference: hdp/measure.py:10-94, 183-194.  All arrays are dense f32 of n elements; in-place
+ * (d_out == d_temp) is allowed.  Results are bit-identical to the reference's Numba / NumPy float32 arithmetic.
+ *
+ *   hdp_b200_heat_index          out[F] = heat_index(temp[F], rh[%])                      the @nb.vectorize ufunc, measure.py:61-94
+ *   hdp_b200_heat_index_measure  out[C] = F->C(heat_index(C->F(temp[C]), rh[%]))          the `{name}_hi` branch, measure.py:183-194;
+ *                                rh_is_fraction != 0: rh is g/g and is scaled by 100 first
+ *   hdp_b200_to_celsius          unit 0 = copy, 1 = Kelvin (temp - 273.15), 2 = Fahrenheit ((temp - 32) / 1.8), measure.py:10-41
+ * ------------------------------------------------------------------------------------------------- */
+int hdp_b200_heat_index(const float *d_temp_f, const float *d_rh_pct, int64_t n, float *d_out_f, void *stream);
+int hdp_b200_heat_index_measure(const float *d_temp_c, const float *d_rh, int64_t n, int rh_is_fraction, float *d_out_c, void *stream);
+int hdp_b200_to_celsius(const float *d_temp, int64_t n, int unit, float *d_out_c, void *stream);
+
 /* Last kernel-launch counters (for bench.py's gpu_launches claim): number of kernels this library has
  * launched since it was loaded. */
 int64_t hdp_b200_launch_count(void);
@@ -153,6 +167,7 @@ int64_t hdp_b200_launch_count(void);
 #define HDP_B200_KERNEL_UNPACK_MASK  5
 #define HDP_B200_KERNEL_THR_SEG      6   /* k_thr_seg */
 #define HDP_B200_KERNEL_THR_RANKED   7   /* k_thr_ranked */
+#define HDP_B200_KERNEL_MEASURE      8   /* k_measure */
 void hdp_b200_timing_enable(int on);
 int  hdp_b200_timing_read(int *ids, float *ms, int cap);
 

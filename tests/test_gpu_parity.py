@@ -325,3 +325,80 @@ def test_host_pipeline_many_chunks(core, monkeypatch, chunk):
     assert np.array_equal(core.metrics_host(xr, thr_h, *args[:-1], None), core.metrics_array(dev(xr), thr_d, *args[:-1], None).cpu().numpy())
     core.host_release()
     assert bits_equal(core.thresholds_host(xb, wt, q), thr_h)          # the context comes back after a release
+
+
+# ------------------------------------------------------------------------------------------ hdp.measure pre-pass (next row)
+def _bits32(a):
+    """float32 bit patterns with every NaN mapped to one pattern (CUDA's single-precision operations return the canonical
+    NaN 0x7fffffff where x86 propagates the operand's payload; which NaN it is carries no meaning)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7fc00000), a.view(np.uint32))
+
+
+def test_heat_index_kernel_matches_reference_kernel(core):
+    # outputs of the reference's own Numba heat_index (tests/golden/measure.npz), bit for bit in float32
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "measure.npz"))
+    got = core.heat_index_array(dev(g["t"].astype(np.float32).ravel()), dev(g["rh"].astype(np.float32).ravel())).cpu().numpy()
+    assert np.array_equal(_bits32(got), _bits32(g["hi"].ravel()))
+
+
+def test_measure_prepass_matches_host_mirror(core):
+    # dense sweep over every branch of the regression (simple formula, full regression, both adjustments, NaN / inf),
+    # odd length (scalar tail + misaligned views), against the NumPy mirror that is itself pinned to the reference kernel
+    from hdp_b200 import measure
+    rng = np.random.default_rng(41)
+    n = 1_000_003
+    tf = rng.uniform(20, 125, n).astype(np.float32)
+    rh = rng.uniform(0, 100, n).astype(np.float32)
+    tf[:7] = [np.nan, np.inf, -np.inf, 80.0, 87.0, 112.0, 95.0]
+    rh[:7] = [50.0, 50.0, 50.0, 13.0, 85.0, 12.999, np.nan]
+    want = measure.heat_index(tf, rh)
+    got = core.heat_index_array(dev(tf), dev(rh)).cpu().numpy()
+    assert np.array_equal(_bits32(got), _bits32(want))
+    # misaligned (offset by one element): the scalar path
+    d_t, d_r = dev(tf), dev(rh)
+    got1 = core.heat_index_array(d_t[1:].contiguous()[:], d_r[1:].contiguous()).cpu().numpy()
+    assert np.array_equal(_bits32(got1), _bits32(want[1:]))
+    # the `{name}_hi` chain of format_standard_measures: C -> F, heat index, F -> C, rh in % and in g/g
+    tc = rng.uniform(-10, 50, n).astype(np.float32)
+    for frac in (False, True):
+        r = (rh / np.float32(100)).astype(np.float32) if frac else rh
+        pct = r * np.float32(100) if frac else r
+        chain = (measure.heat_index((tc * 1.8) + 32, pct) - 32) / 1.8
+        assert chain.dtype == np.float32
+        got = core.heat_index_measure_array(dev(tc), dev(r), rh_is_fraction=frac).cpu().numpy()
+        assert np.array_equal(_bits32(got), _bits32(chain))
+    # unit conversions (float32 array arithmetic in the reference)
+    k = (tc + np.float32(273.15)).astype(np.float32)
+    want_k = k.copy(); want_k -= 273.15
+    assert np.array_equal(_bits32(core.to_celsius_array(dev(k), "K").cpu().numpy()), _bits32(want_k))
+    f = ((tc * 1.8) + 32).astype(np.float32)
+    assert np.array_equal(_bits32(core.to_celsius_array(dev(f), "degF").cpu().numpy()), _bits32((f - 32) / 1.8))
+    assert np.array_equal(_bits32(core.to_celsius_array(dev(tc), "degC").cpu().numpy()), _bits32(tc))
+    assert core.heat_index_array(dev(tf[:0]), dev(rh[:0])).numel() == 0
+
+
+def test_measure_prepass_full_size_throughput(core, capsys):
+    # one measure of cmip6_1deg (64 800 x 31 390 float32): in-place chain, result spot-checked; prints the achieved GB/s
+    n = 64800 * 31390
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    tc = torch.empty(n, dtype=torch.float32, device="cuda").uniform_(-10, 50, generator=g)
+    rh = torch.empty(n, dtype=torch.float32, device="cuda").uniform_(0, 100, generator=g)
+    out = torch.empty_like(tc)
+    core.heat_index_measure_array(tc, rh, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        core.heat_index_measure_array(tc, rh, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    from hdp_b200 import measure
+    idx = torch.randint(0, n, (200_000,), device="cuda")
+    t_s, r_s = tc[idx].cpu().numpy(), rh[idx].cpu().numpy()
+    want = (measure.heat_index((t_s * 1.8) + 32, r_s) - 32) / 1.8
+    assert np.array_equal(_bits32(out[idx].cpu().numpy()), _bits32(want))
+    with capsys.disabled():
+        print(f"\n[k_measure] {n} elements, {ms:.2f} ms, {12 * n / ms / 1e6:.0f} GB/s (12 B per element)")

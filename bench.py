@@ -126,8 +126,9 @@ def host_cores() -> int:
 def cpu_tables(wl):
     from hdp_b200 import _tables as tb
     wt = wl.window_tables()
-    st = wl.seasons()
-    return wt, tb.doy_map(wl.run_axis().dayofyr), st
+    if not wl.run_years:
+        return wt, None, None
+    return wt, tb.doy_map(wl.run_axis().dayofyr), wl.seasons()
 
 
 def cpu_pass(wl, base, run, is_south, threads=None):
@@ -228,15 +229,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     wl = workloads.get(args.workload)
-    wt, st = wl.window_tables(), wl.seasons()
-    dm = tb.doy_map(wl.run_axis().dayofyr)
+    wt = wl.window_tables()
+    st = wl.seasons() if wl.run_years else None                       # thresholds-only workloads (era5_025deg) have no run
+    dm = tb.doy_map(wl.run_axis().dayofyr) if wl.run_years else None
     lat, _ = synth.grid_latitudes(wl.n_lat, wl.n_lon)
     if args.cells:
         lat = lat[np.linspace(0, wl.cells - 1, args.cells).astype(np.int64)]
     C = lat.size
     south = torch.as_tensor((lat < 0).astype(np.uint8), device=dev)
     q, defs = wl.percentiles, wl.defs
-    P, D, Y, n_doy = len(q), len(defs), st.n_years, wt.n_doy
+    P, D, Y, n_doy = len(q), len(defs), (st.n_years if st else 0), wt.n_doy
     offsets = [5.0, -5.0, 0.0][: wl.measures]                       # tmax / tmin / tavg
 
     # weak scaling: every rank owns a full grid (its own ensemble member, seeded by rank), no collective on the path

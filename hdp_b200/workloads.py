@@ -69,6 +69,8 @@ class Workload:
         return C * (4 * len(self.base_axis()) + 8 * wt.n_doy * len(self.percentiles))
 
     def bytes_metrics(self, cells: int = None) -> int:
+        if not self.run_years:
+            return 0
         C = self.cells if cells is None else cells
         n_doy = self.window_tables().n_doy
         P, D, Y = len(self.percentiles), len(self.defs), self.seasons().n_years

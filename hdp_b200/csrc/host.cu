@@ -121,18 +121,20 @@ static int upload_cells(const float *h, int64_t T, int64_t ld_t, int64_t ld_c, i
     return HDP_B200_OK;
 }
 
-// Cells per chunk: ~64 MB of input per chunk keeps the pipeline's fill and drain (one chunk each) near one percent of
-// a CMIP-sized call while copy rows stay >= 2 KB and the kernel grids fill the GPU; a multiple of 32 cells (warp = 32
-// cells).  Measured on B200 / PCIe Gen5 (tools/e2e_breakdown.py): 1 024 .. 4 096 cells per chunk are within 2 %.
-static int64_t pick_chunk(int64_t C, size_t in_bytes_per_cell)
+// Cells per chunk: small enough that the pipeline's fill and drain (one chunk each) stay near one percent of a CMIP-sized
+// call, large enough that copy rows stay >= 2 KB and that a chunk's kernels (a k_scan launch takes >= 1.5 ms however few
+// cells it has: every warp walks the whole series) stay shorter than its H2D copy; a multiple of 32 cells (warp = 32
+// cells).  Measured on B200 / PCIe Gen5 (tools/e2e_breakdown.py): thresholds 1 024 .. 4 096 cells per chunk within 2 %,
+// metrics 1 024 .. 4 096 within 2 %, 512 cells 17 % slower (kernel-bound).
+static int64_t pick_chunk(int64_t C, size_t in_bytes_per_cell, size_t target_bytes)
 {
     if (const char *e = std::getenv("HDP_B200_HOST_CHUNK_CELLS")) {
         const int64_t v = std::atoll(e);
         if (v > 0) return std::min<int64_t>(std::max<int64_t>(32, v / 32 * 32), std::max<int64_t>(C, 1));
     }
-    int64_t chunk = (int64_t)((size_t)64 << 20) / (int64_t)std::max<size_t>(in_bytes_per_cell, 1);
-    chunk = std::max<int64_t>(512, chunk / 32 * 32);
-    if (C > 2048) chunk = std::min(chunk, ((C + 3) / 4 + 31) / 32 * 32);       // at least 4 chunks once there is work to overlap
+    int64_t chunk = (int64_t)target_bytes / (int64_t)std::max<size_t>(in_bytes_per_cell, 1);
+    chunk = std::max<int64_t>(1024, chunk / 32 * 32);
+    if (C > 4096) chunk = std::min(chunk, ((C + 3) / 4 + 31) / 32 * 32);       // at least 4 chunks once there is work to overlap
     return std::min(chunk, std::max<int64_t>(C, 1));
 }
 
@@ -173,7 +175,7 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
     if ((rc = ctx->init())) return rc;
 
     const size_t out_per_cell = (size_t)n_doy * P * sizeof(double);
-    const int64_t chunk = pick_chunk(C, (size_t)T_b * sizeof(float));
+    const int64_t chunk = pick_chunk(C, (size_t)T_b * sizeof(float), (size_t)64 << 20);
     const int64_t dl_t = ld_c == 1 ? chunk : 1, dl_c = ld_c == 1 ? 1 : T_b;
     const size_t ws_bytes = hdp_b200_thresholds_workspace_bytes(chunk, T_b, dl_t, dl_c, n_doy, n_y, W, P);
     if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
@@ -223,7 +225,7 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
 
     const size_t thr_per_cell = (size_t)n_doy * P * sizeof(double);
     const size_t rows = (size_t)4 * P * D * Y;                                 // output rows of C cells each
-    const int64_t chunk = pick_chunk(C, (size_t)T * sizeof(float) + thr_per_cell);
+    const int64_t chunk = pick_chunk(C, (size_t)T * sizeof(float) + thr_per_cell, (size_t)320 << 20);
     const int64_t dl_t = ld_c == 1 ? chunk : 1, dl_c = ld_c == 1 ? 1 : T;
     const size_t ws_bytes = hdp_b200_metrics_workspace_bytes(chunk, T, dl_t, dl_c, n_doy, P, D, Y, h_doy_map);
     if ((rc = ctx->ws.reserve(ws_bytes))) return rc;

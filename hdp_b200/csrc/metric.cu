@@ -182,12 +182,15 @@ constexpr int kScanQueueWords = 3 * kScanQ * 32;                  // u32 per war
 //
 //  A (warp-synchronous over the hot words, in time order): the lanes read word k of their cells (one coalesced
 //    load, prefetched four words ahead), DROP THE RUNS THAT CANNOT MATTER and queue what is left of the word, as run
-//    start / run end bit masks, in a per-lane ring buffer in shared memory.  A run shorter than every definition's
-//    min_duration whose preceding break is longer than every definition's max_break only clears in_heatwave for all
-//    definitions (reference index_heatwaves, hdp/metric.py:43-58: branch A needs the length, C and D need
-//    in_heatwave) - and the longer break the next run then sees does exactly the same, so such runs are removed with
-//    bit operations on the word and its neighbours (long = member of min_duration consecutive hot days; near = the
-//    run starts within max_break + 1 days of a hot day; keep = long | near, flood-filled over the run by an add).
+//    start / run end bit masks, in a per-lane ring buffer in shared memory.  Let lmin = min over definitions of
+//    min_duration and bmax = max over definitions of max_break, call a run long if it has >= lmin days, and a cluster a
+//    maximal sequence of runs whose breaks are all <= bmax.  Before the first long run of its cluster a run finds
+//    in_heatwave clear for every definition (the break before the cluster cleared it, reference index_heatwaves,
+//    hdp/metric.py:43-58) and, being short, leaves it clear: branch A needs the length, C and D need in_heatwave.  It
+//    changes no state and gets no label - and the longer break the next kept run then sees clears in_heatwave just the
+//    same - so only the runs from the first long run of a cluster on are kept: keep_i = long_i | (near_i & keep_(i-1)).
+//    This is evaluated with bit operations on the word and its neighbours (b = days of long runs; G = days at most bmax
+//    after a hot day, so a cluster is one contiguous run of G; an add floods each cluster upwards from its long days).
 //    Where a neighbouring word is not known yet the run is kept.  Words without a surviving run start or end are
 //    not queued at all.
 //  B (lane-asynchronous): every lane pops the runs of its own queue and advances ALL definitions' state machines
@@ -312,7 +315,7 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     const uint32_t *hp_ahead = hp + 4 * C;                        // word k_ext + 4
     const int64_t pf_off = (int64_t)kScanQ * C;
     uint32_t tail = 0u, a_tail = 0u;                              // hot days / `long` seeds of the 32 days before word k_ext (bit 31 = yesterday)
-    uint32_t carry_keep = 0u, open_f = 0u;                        // a kept `near` run / any kept run reaches the end of the previous word
+    uint32_t live_in = 0u, open_f = 0u;                           // a live cluster / a kept run reaches the end of the previous word
     uint32_t qr = 0u, qw = 0u;                                    // ring buffer read / write counters
     const bool f_on = tabs.f_on != 0;
     const int f_lmin = tabs.f_lmin, f_bmax = tabs.f_bmax;
@@ -332,9 +335,8 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                     lo = cur | (fut << nb);
                     hi = (fut >> (32 - nb)) | (uint32_t)wm.w;
                 }
-                // a_j: days j .. j + lmin - 1 are all hot;  b_j: day j belongs to lmin consecutive hot days
-                // near_j: one of the days j - 2 .. j - bmax - 1 is hot
-                uint32_t a = lo, near = 0u;
+                // a_j: days j .. j + lmin - 1 are all hot;  b_j: day j belongs to lmin consecutive hot days (a long run)
+                uint32_t a = lo;
 #pragma unroll
                 for (int j = 1; j < 4; j++) if (j < f_lmin) a &= __funnelshift_r(lo, hi, j);
                 for (int j = 4; j < f_lmin; j++) a &= __funnelshift_r(lo, hi, j);
@@ -343,14 +345,19 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
 #pragma unroll
                 for (int j = 1; j < 4; j++) if (j < f_lmin) b |= __funnelshift_l(a_tail, a, j);
                 for (int j = 4; j < f_lmin; j++) b |= __funnelshift_l(a_tail, a, j);
+                // G_j: day j is hot or at most bmax days after a hot day - runs whose breaks are all <= bmax form one
+                // contiguous cluster of G
+                uint32_t G = cur;
 #pragma unroll
-                for (int j = 2; j < 5; j++) if (j <= f_bmax + 1) near |= __funnelshift_l(tail, cur, j);
-                for (int j = 5; j <= f_bmax + 1; j++) near |= __funnelshift_l(tail, cur, j);
-                const uint32_t prev = __funnelshift_l(tail, cur, 1);                   // day j - 1 is hot
-                const uint32_t ns = (cur & ~prev & near) | (carry_keep & cur & 1u);
-                const uint32_t fill = ((cur + ns) ^ cur) & cur;    // the whole run above every kept run start
-                keep = (b | fill) & cur;
-                carry_keep = fill >> (nb - 1);                     // (bit 0 is what is used)
+                for (int j = 1; j < 4; j++) if (j <= f_bmax) G |= __funnelshift_l(tail, cur, j);
+                for (int j = 4; j <= f_bmax; j++) G |= __funnelshift_l(tail, cur, j);
+                G &= vmask;
+                // a cluster matters from its first long run on: flood every cluster upwards from its long days (and from
+                // day 0 if the cluster was already live at the end of the previous word); the add carries through G
+                const uint32_t seed = b | (live_in & G & 1u);
+                const uint32_t flooded = (((G + seed) ^ G) & G) | seed;
+                keep = flooded & cur;
+                live_in = flooded >> (nb - 1);                     // (bit 0 is what is used)
                 tail = nb == 32 ? cur : __funnelshift_r(tail, cur, nb);
                 a_tail = nb == 32 ? a : __funnelshift_r(a_tail, a, nb);
             }

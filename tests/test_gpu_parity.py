@@ -287,6 +287,39 @@ def test_metrics_definition_counts_and_ranges(core, D):
     _mask_case(core, masks, defs.tolist(), seasons_n, seasons_s, rng.integers(0, 2, C))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_run_filter_random_definitions(core, seed):
+    # definitions that switch k_scan's run filter ON (every min_duration >= 2) with many (lmin, bmax) pairs, hot-day
+    # densities from sparse to dense, a calendar whose day-of-year words are short (leap years / 360-day), both hemispheres
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(1000 + seed)
+    cal = ["noleap", "standard", "360_day", "standard"][seed % 4]
+    ax = tb.TimeAxis.date_range("2001-01-01", "2012-12-30" if cal == "360_day" else "2012-12-31", cal)
+    T, C = len(ax), 97
+    lmin, bmax = int(rng.integers(2, 13)), int(rng.integers(0, 10))
+    D = int(rng.integers(1, 12))
+    defs = np.stack([rng.integers(lmin, lmin + 6, D), rng.integers(0, bmax + 1, D), rng.integers(0, 4, D)], axis=1)
+    defs[rng.integers(0, D)] = [lmin, bmax, int(rng.integers(0, 3))]
+    dens = rng.uniform(0.02, 0.9, C)
+    # AR(1)-like persistence so that long runs exist at every density
+    z = rng.standard_normal((T, C))
+    for t in range(1, T):
+        z[t] = 0.8 * z[t - 1] + 0.6 * z[t]
+    thr_q = np.array([np.quantile(z[:, c], 1 - dens[c]) for c in range(C)])
+    masks = z > thr_q[None, :]
+    masks[:, 0] = True                                        # one run over the whole series
+    masks[:, 1] = False
+    masks[:, 2] = (np.arange(T) % (lmin + bmax + 1)) < lmin   # exactly lmin hot days, then bmax + 1 cold: every run starts a heatwave
+    masks[:, 3] = (np.arange(T) % (lmin + bmax)) < lmin - 1   # always one day short, breaks exactly bmax + 1 ... bmax
+    st = tb.hemisphere_ranges(ax)
+    x = masks.astype(np.float32)
+    thr = np.full((C, int(ax.dayofyr.max()), 1), 0.5)
+    args = (tb.doy_map(ax.dayofyr), defs.tolist(), st.north, st.south, rng.integers(0, 2, C).astype(np.uint8))
+    out = ref_layout(core.metrics_array(dev(x), dev(thr), *args))
+    want = oracle.metrics_batch(x, thr, *args)
+    assert np.array_equal(out, want)
+
+
 def test_metrics_tiny_and_empty(core):
     one = _mask_case(core, [[1]], [[1, 0, 0], [2, 0, 0]], [[0, 1]], [[0, 1]], None)
     assert one[0, :, 0, 0, 0].tolist() == [1, 0]

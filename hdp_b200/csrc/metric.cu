@@ -247,7 +247,10 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     if (cg * 32 >= C) return;                                     // warp-uniform
     const bool alive = cg * 32 + lane < C;                        // lanes past the last cell shadow it (the warp votes with all 32 lanes)
     const int64_t c = alive ? cg * 32 + lane : C - 1;
-    uint32_t *q_st = queues + (tid >> 5) * kScanQueueWords + lane, *q_en = q_st + kScanQ * 32, *q_t0 = q_en + kScanQ * 32;
+    // 32-bit shared-state-space addresses: queue slot i of this lane is q_st + 128 i (run starts), + kQEn (run ends), + kQT0 (first day)
+    const uint32_t q_st = smem_u32(queues + (tid >> 5) * kScanQueueWords + lane);
+    constexpr uint32_t kQEn = kScanQ * 128, kQT0 = 2 * kScanQ * 128;
+    const uint32_t ge_a = smem_u32(ge_s), brk_a = smem_u32(brk_s), meta_a = smem_u32(word_meta);
 
     const bool south = is_south != nullptr && is_south[c] != 0;
     const int4 *seas = south ? seasons_south : seasons_north;
@@ -322,8 +325,8 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
 
     auto extract = [&](int n_words, bool live) {
         for (int i = 0; i < n_words; i++) {
-            const int4 wm = word_meta[k_ext];                     // warp-uniform
-            const int t0 = wm.x, nb = wm.y;
+            const uint4 wm = lds_v4(meta_a + 16u * (uint32_t)k_ext);   // warp-uniform
+            const int t0 = (int)wm.x, nb = (int)wm.y;
             const uint32_t cur = w0;
             const uint32_t vmask = 0xffffffffu >> (32 - nb);
             uint32_t keep = cur;
@@ -365,8 +368,8 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
             const uint32_t st = keep & ~prevk, en = ~keep & prevk & vmask;
             open_f = (keep >> (nb - 1)) & 1u;
             if (live && (st | en) != 0u) {
-                const uint32_t slot = (qw & (kScanQ - 1)) * 32;
-                q_st[slot] = st; q_en[slot] = en; q_t0[slot] = (uint32_t)t0;
+                const uint32_t slot = q_st + (qw & (kScanQ - 1)) * 128u;
+                sts_u32(slot, st); sts_u32(slot + kQEn, en); sts_u32(slot + kQT0, (uint32_t)t0);
                 qw++;
             }
             w0 = w1; w1 = w2; w2 = w3;
@@ -391,32 +394,33 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     for (;;) {
         const bool open = ys < n_seasons;
         if (!__any_sync(0xffffffffu, open)) break;
-        bool done = !open;                                        // this lane has nothing more to do before the season closes
+        // lane state inside a season: 0 = consuming runs, 1 = done (nothing more to do before the season closes),
+        // 2 = starved (its queue is empty and there are words left to extract)
+        int state = open ? 0 : 1;
         if (!open) qr = qw;                                       // a lane without seasons left drops what it has queued
         if (open && pend_lab) {
             const int days = min(pend_e, b_cur) - max(pend_s, a_cur);
             if (days > 0) account(pend_lab, (uint32_t)days);
-            if (pend_e <= b_cur) pend_lab = 0u; else done = true;
+            if (pend_e <= b_cur) pend_lab = 0u; else state = 1;
         }
         for (;;) {
-            bool starved = false;
-            while (__any_sync(0xffffffffu, !done && !starved)) {
-                if (!done && !starved && ends == 0u) {
+            if (state == 2) state = 0;
+            while (__any_sync(0xffffffffu, state == 0)) {
+                if (state == 0 && ends == 0u) {
                     // ---- the word is used up: take the next one from the queue ----
                     if (starts) { run_start = t0 + __ffs(starts) - 1; starts = 0u; }   // at most one start is left: the run stays open
                     if (qr == qw) {
-                        if (k_ext > K) done = true;               // series exhausted
-                        else starved = true;
+                        state = k_ext > K ? 1 : 2;                // series exhausted : starved
                     } else {
-                        const uint32_t slot = (qr & (kScanQ - 1)) * 32;
-                        starts = q_st[slot]; ends = q_en[slot]; t0 = (int)q_t0[slot];
+                        const uint32_t slot = q_st + (qr & (kScanQ - 1)) * 128u;
+                        starts = lds_u32(slot); ends = lds_u32(slot + kQEn); t0 = (int)lds_u32(slot + kQT0);
                         qr++;
                     }
                 }
-                if (!done && !starved && ends != 0u) {
+                if (state == 0 && ends != 0u) {
                     // ---- the next hot run [s, e): leave it queued if it starts after this season ----
                     const int s = run_start >= 0 ? run_start : t0 + __ffs(starts) - 1;
-                    if (s >= b_cur) done = true;
+                    if (s >= b_cur) state = 1;
                     else {
                         const int e = t0 + __ffs(ends) - 1;
                         ends &= ends - 1;
@@ -425,8 +429,8 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                         prev_e = e;
 
                         // reference index_heatwaves branches A-D for all definitions at once (metric.py:43-58)
-                        const uint32_t ge = ge_s[min(len, ge_cap)];   // len >= min_duration
-                        inhw &= ~brk_s[min(gap, brk_cap)];            // B: the break before this run was too long
+                        const uint32_t ge = lds_u32(ge_a + 4u * (uint32_t)min(len, ge_cap));    // len >= min_duration
+                        inhw &= ~lds_u32(brk_a + 4u * (uint32_t)min(gap, brk_cap));            // B: the break before this run was too long
                         const uint32_t A = ~inhw & ge;                // A: a new heatwave starts
                         const uint32_t Cm = inhw & sublt;             // C: subsequent event of the current heatwave
                         const uint32_t Dm = inhw & ~sublt;            // D: subsequent events used up
@@ -445,17 +449,17 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                         }
                         const int days = min(e, b_cur) - max(s, a_cur);
                         if (lab != 0u && days > 0) account(lab, (uint32_t)days);
-                        if (lab != 0u && e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; done = true; }
+                        if (lab != 0u && e > b_cur) { pend_lab = lab; pend_s = s; pend_e = e; state = 1; }
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, !done)) break;           // every lane has reached the end of its season
+            if (!__any_sync(0xffffffffu, state != 1)) break;      // every lane has reached the end of its season
             // some lane ran out of queued words: extract as many as fit the fullest queue (a word adds at most one entry)
             const int room = kScanQ - (int)__reduce_max_sync(0xffffffffu, open ? qw - qr : 0u);
             if (room == 0) break;                                 // blocked by a lane waiting for its next season: close those first
             extract(min(room, K + 1 - k_ext), open);
         }
-        if (open && done) flush();
+        if (open && state == 1) flush();
     }
 }
 

@@ -191,3 +191,32 @@ def test_array_level_seams_match_reference_signatures():
     out = metric.compute_heatwave_metrics(temps[0, 0], got[0, 0, :, 0], dm, 3, 1, 1, seasons)
     assert out.shape == (4, 4) and out.dtype == np.int64
     assert np.array_equal(out, oracle.compute_heatwave_metrics(temps[0, 0], got[0, 0, :, 0], dm, 3, 1, 1, seasons))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("members,years", [(3, 4), (40, 20)])
+def test_member_dimension_is_pooled_into_the_sample(members, years):
+    """hdp/threshold.py:114-119: a `member` dimension is concatenated along time, so every window pools
+    W x years x members samples (CESM2-LENS style).  (3, 4): the segment kernel; (40, 20): 15 x 800 = 12 000 samples per
+    window, which only the generic gather + sort kernel takes."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import oracle
+    from hdp_b200 import threshold
+    rng = np.random.default_rng(members)
+    ax = tb.TimeAxis.date_range("1961-01-01", f"{1960 + years}-12-31", "noleap")
+    lon, lat = np.array([0.0, 120.0]), np.array([-30.0, 0.0, 30.0])
+    vals = (15 + 8 * np.sin(2 * np.pi * (ax.dayofyr - 110) / 365)[None, None, None, :]
+            + 3 * rng.standard_normal((members, 2, 3, len(ax)))).astype(np.float32)
+    da = xr.DataArray(vals, dims=["member", "lon", "lat", "time"],
+                      coords={"member": np.arange(members), "lon": lon, "lat": lat, "time": ax},
+                      name="tas", attrs={"units": "degC", "hdp_type": "measure", "baseline_variable": "tas"})
+    q = np.array([0.5, 0.9, 0.95, 0.99])
+    thr = threshold.compute_threshold(da, q)["tas_threshold"]
+    assert tuple(thr.dims) == ("lon", "lat", "doy", "percentile") and thr.shape == (2, 3, 365, 4)
+    pooled = np.concatenate([vals[m] for m in range(members)], axis=-1).reshape(6, -1).T     # members one after another along time
+    wt = tb.window_tables(np.tile(ax.dayofyr, members), 7)
+    assert wt.n_y == members * years
+    want = oracle.thresholds_batch(np.ascontiguousarray(pooled), wt.window_samples(), q)
+    assert bits_equal(xr.values_of(thr).reshape(6, 365, 4), want)

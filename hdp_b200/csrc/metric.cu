@@ -239,12 +239,15 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     }
     __syncthreads();
 
-    // warp -> (group of 32 cells, percentile): every warp of the grid has work
+    // warp -> (percentile, group of 32 cells), percentile-major: the warps of a CTA work on the same percentile, so they
+    // have similar numbers of runs and the CTA's shared memory is not held by one slow warp; the first percentile (with
+    // sorted percentiles the one with the most hot days) is scheduled first, the lightest last, which shortens the tail
     const int lane = tid & 31;
+    const int64_t n_cg = (C + 31) / 32;
     const int64_t wg = (int64_t)blockIdx.x * kScanWarps + (tid >> 5);
-    const int64_t cg = wg / P;
-    const int p = (int)(wg - cg * P);
-    if (cg * 32 >= C) return;                                     // warp-uniform
+    const int p = (int)(wg / n_cg);
+    const int64_t cg = wg - (int64_t)p * n_cg;
+    if (p >= P) return;                                           // warp-uniform
     const bool alive = cg * 32 + lane < C;                        // lanes past the last cell shadow it (the warp votes with all 32 lanes)
     const int64_t c = alive ? cg * 32 + lane : C - 1;
     // 32-bit shared-state-space addresses: queue slot i of this lane is q_st + 128 i (run starts), + kQEn (run ends), + kQT0 (first day)

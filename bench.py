@@ -30,7 +30,7 @@ UNIT = "grid-cell-years/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cmip6_1deg")
@@ -67,8 +67,11 @@ def measured_traffic(label: str, cells: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  It is started before the warm-up (nvidia-smi needs a few
+    hundred ms to deliver its first line) and `stop(t0, t1)` keeps the samples whose timestamps fall inside the timed region
+    [t0, t1] (time.time()); a region shorter than the sampling period falls back to the samples within 0.5 s around it, which
+    were taken under the same load (warm-up steps before, end-to-end steps after)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_id: str):
@@ -76,14 +79,16 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", gpu_id, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=self.file, stderr=subprocess.DEVNULL)
+                                          "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.15)                                   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -91,23 +96,27 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.file.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         self.file.close()
         os.unlink(self.file.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        where = "timed region"
+        if not inside:
+            inside = [r for r in rows if t0 - 0.5 <= r[0] <= t1 + 0.5]
+            where = "within 0.5 s of the timed region (region shorter than the sampling period)"
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), sampled=where)
         return out
 
 
@@ -263,28 +272,30 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-
     gpu_id = str(getattr(torch.cuda.get_device_properties(dev), "uuid", local_rank))
     if not gpu_id.startswith("GPU-") and len(gpu_id) > 8:
         gpu_id = "GPU-" + gpu_id
     sampler = ClockSampler(gpu_id) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
     _core.timing_enable(True)
     _core.timing_read()
     launches0 = _core.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     sync_all()
+    t_region1 = time.time()
     elapsed_ms = e0.elapsed_time(e1)
     launches = _core.launch_count() - launches0
     kern = _core.timing_read()
     _core.timing_enable(False)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -329,6 +329,35 @@ def test_metrics_tiny_and_empty(core):
     assert tuple(out.shape) == (4, 2, 1, 1, 0)
 
 
+# ------------------------------------------------------------------------------------------ limits
+def test_maximum_percentiles_and_definitions(core):
+    # HDP_B200_MAX_PERCENTILES = HDP_B200_MAX_DEFINITIONS = 32: the largest sweep one call takes, and the error beyond it
+    from hdp_b200 import _tables as tb, _lib
+    rng = np.random.default_rng(77)
+    base_ax = tb.TimeAxis.date_range("1961-01-01", "1968-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2006-12-31", "noleap")
+    C = 45
+    wt = tb.window_tables(base_ax.dayofyr, 7)
+    xb = (12 + 9 * np.sin(2 * np.pi * (base_ax.dayofyr[:, None] - 110) / 365) + 3 * rng.standard_normal((len(base_ax), C))).astype(np.float32)
+    xr_ = (13 + 9 * np.sin(2 * np.pi * (run_ax.dayofyr[:, None] - 110) / 365) + 3 * rng.standard_normal((len(run_ax), C))).astype(np.float32)
+    q = np.linspace(0.5, 0.995, 32)
+    thr = core.thresholds_array(dev(xb), wt, q)
+    want_thr = oracle.thresholds_batch(xb, wt.window_samples(), q)
+    assert bits_equal(thr.cpu().numpy(), want_thr)
+    defs = [[int(a), int(b), int(c)] for a, b, c in zip(rng.integers(1, 7, 32), rng.integers(0, 3, 32), rng.integers(0, 3, 32))]
+    st = tb.hemisphere_ranges(run_ax)
+    args = (tb.doy_map(run_ax.dayofyr), defs, st.north, st.south, (rng.random(C) < 0.5).astype(np.uint8))
+    out = core.metrics_array(dev(xr_), thr, *args)
+    assert tuple(out.shape) == (4, 32, 32, st.n_years, C)
+    assert np.array_equal(ref_layout(out), oracle.metrics_batch(xr_, want_thr, *args))
+    with pytest.raises(_lib.HdpB200Error) as e:
+        core.thresholds_array(dev(xb), wt, np.linspace(0.5, 0.99, 33))
+    assert e.value.code == -2                                  # HDP_B200_ERR_UNSUPPORTED
+    with pytest.raises(_lib.HdpB200Error) as e:
+        core.metrics_array(dev(xr_), thr, args[0], defs + [[3, 0, 0]], *args[2:])
+    assert e.value.code == -2
+
+
 # ------------------------------------------------------------------------------------------ host pipeline
 @pytest.mark.parametrize("chunk", ["32", "64", "96"])
 def test_host_pipeline_many_chunks(core, monkeypatch, chunk):

@@ -132,6 +132,25 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(gpu_id: str):
+    """Multi-GPU boxes have several NUMA nodes: run this rank on the cores next to its GPU, so that the pinned host buffers of
+    the end-to-end leg are allocated (first touch) in the memory its PCIe root is attached to.  Returns the previous affinity
+    (the CPU baseline leg restores it: it is meant to use every host core)."""
+    try:
+        import pynvml
+        previous = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByUUID(gpu_id) if gpu_id.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(gpu_id))
+        n_words = (max(previous) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1} & previous
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return previous
+    except Exception:                                      # no NVML / no permission: stay where we are
+        return None
+
+
 def cpu_tables(wl):
     from hdp_b200 import _tables as tb
     wt = wl.window_tables()
@@ -234,6 +253,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hdp_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    gpu_id = str(getattr(torch.cuda.get_device_properties(dev), "uuid", local_rank))
+    if not gpu_id.startswith("GPU-") and len(gpu_id) > 8:
+        gpu_id = "GPU-" + gpu_id
+    full_affinity = bind_to_gpu_numa_node(gpu_id) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -272,9 +295,6 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    gpu_id = str(getattr(torch.cuda.get_device_properties(dev), "uuid", local_rank))
-    if not gpu_id.startswith("GPU-") and len(gpu_id) > 8:
-        gpu_id = "GPU-" + gpu_id
     sampler = ClockSampler(gpu_id) if rank == 0 else None
     for _ in range(args.warmup):
         step()
@@ -344,7 +364,8 @@ def main():
         "config": {"workload": wl.name, "description": wl.description, "cells_per_gpu": int(C), "base_days": len(wl.base_axis()),
                    "run_days": len(wl.run_axis()) if wl.run_years else 0, "measures": wl.measures, "percentiles": P, "definitions": D,
                    "window_radius": wl.radius, "sharding": f"cells x{world} (one full grid per GPU, no collective)",
-                   "l2": "inputs per step far larger than L2 (no flush needed)"},
+                   "l2": "inputs per step far larger than L2 (no flush needed)",
+                   "host_numa_binding": bool(full_affinity)},
         "gpu_launches": int(launches),
         "step_roofline": {"algorithmic_bytes_per_step": int(step_bytes), "achieved_gbs": step_gbs, "frac": step_gbs / peak},
         "roofline": roofline,
@@ -391,6 +412,8 @@ def main():
 
     # ---- cpu_baseline: oracle port on a bounded sample of measure 0, all host cores, rank 0 only; also a parity check
     if rank == 0 and not args.no_cpu:
+        if full_affinity:
+            os.sched_setaffinity(0, full_affinity)         # the CPU baseline uses every host core
         cores = host_cores()
         n_probe = min(C, max(cores, 8))
         sel = np.linspace(0, C - 1, n_probe).astype(np.int64)

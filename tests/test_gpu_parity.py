@@ -320,6 +320,23 @@ def test_run_filter_random_definitions(core, seed):
     assert np.array_equal(out, want)
 
 
+def test_scan_queue_pressure_with_unrelated_season_tables(core):
+    # northern and southern tables whose seasons lie thousands of days apart, in one warp: lanes that wait for their next
+    # season sit on full word queues while the others starve (k_scan's blocked path: close the waiting lanes' seasons
+    # first), lanes run out of seasons long before the series ends (their queues are dropped), seasons of unequal counts
+    rng = np.random.default_rng(321)
+    T, C = 6000, 50
+    masks = rng.random((T, C)) < rng.uniform(0.3, 0.9, C)[None, :]
+    masks[:, 0] = True
+    defs = [[3, 0, 0], [3, 1, 1], [2, 2, 3], [4, 1, 0], [6, 2, 1]]
+    north = [[0, 90], [100, 130], [3000, 3200], [3200, 3210], [5900, 6000]]
+    south = [[1400, 2100], [2500, 2600], [2600, 2601], [4000, 5000], [5990, 6000]]
+    _mask_case(core, masks, defs, north, south, rng.integers(0, 2, C))
+    _mask_case(core, masks, defs, north[:2] + [[150, 160], [170, 180], [190, 200]], south, rng.integers(0, 2, C))
+    _mask_case(core, masks, defs, north, south, np.zeros(C, np.uint8))
+    _mask_case(core, masks, defs, north, south, np.ones(C, np.uint8))
+
+
 def test_metrics_tiny_and_empty(core):
     one = _mask_case(core, [[1]], [[1, 0, 0], [2, 0, 0]], [[0, 1]], [[0, 1]], None)
     assert one[0, :, 0, 0, 0].tolist() == [1, 0]

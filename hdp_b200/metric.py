@@ -67,6 +67,23 @@ def _year_times(years: np.ndarray, calendar: str):
     return _tables.TimeAxis(np.asarray(years, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), calendar)
 
 
+def _widen_int64(a: np.ndarray) -> np.ndarray:
+    """uint16 -> int64 of one metric plane ([P, D, Y, C], C-contiguous).  The reference's metrics are int64
+    (hdp/tests/test_workflow.py:57); at CMIP scale that is 2.7 GB in and 10.7 GB out per measure, so the widening is split
+    over the leading axis across threads (NumPy releases the GIL inside the copy)."""
+    out = np.empty(a.shape, dtype=np.int64)
+    n = a.shape[0] if a.ndim else 0
+    if a.size < (1 << 22) or n < 2:
+        np.copyto(out, a, casting="unsafe")
+        return out
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, min(n, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    with ThreadPoolExecutor(workers) as pool:
+        list(pool.map(lambda i: np.copyto(out[i], a[i], casting="unsafe"), range(n)))
+    return out
+
+
 def compute_individual_metrics(measure, threshold, hw_definitions: list, include_threshold: bool = True, check_variables: bool = True):
     """metric.py:372-506."""
     time_axis = time_axis_of(measure)
@@ -114,8 +131,9 @@ def compute_individual_metrics(measure, threshold, hw_definitions: list, include
     dims = ["percentile", "definition", *cell_dims, "time"]
     data_vars = {}
     for i, name in enumerate(_core.METRIC_NAMES):                   # HWF=0, HWN=1, HWD=2, HWA=3, :454-461
-        plane = out[i].transpose(0, 1, 3, 2).reshape(P, D, *cell_shape, Y)              # view: no host transposition
-        data_vars[name] = xr.DataArray(plane.astype(np.int64), dims=dims, coords=coords)
+        wide = _widen_int64(out[i])                                 # [P, D, Y, C] uint16 -> int64, the reference's dtype
+        plane = wide.transpose(0, 1, 3, 2).reshape(P, D, *cell_shape, Y)                # view: no host transposition
+        data_vars[name] = xr.DataArray(plane, dims=dims, coords=coords)
     ds = xr.Dataset(data_vars)
     ds.attrs.update({
         "description": f"Heatwave metric dataset generated by Heatwave Diagnostics Package (HDP v{get_version()})",

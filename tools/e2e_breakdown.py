@@ -1,5 +1,5 @@
 """Wall time of the two host-buffer entry points on one measure of cmip6_1deg (pinned host buffers).
-    python tools/e2e_breakdown.py [cells]"""
+    python tools/e2e_breakdown.py [cells] [--pageable]      (--pageable: ordinary NumPy memory instead of pinned buffers)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,16 +9,20 @@ wl = workloads.get("cmip6_1deg")
 wt, st = wl.window_tables(), wl.seasons()
 dm = tb.doy_map(wl.run_axis().dayofyr)
 lat, _ = synth.grid_latitudes(wl.n_lat, wl.n_lon)
-if len(sys.argv) > 1:
-    lat = lat[np.linspace(0, wl.cells - 1, int(sys.argv[1])).astype(np.int64)]
+PAGEABLE = "--pageable" in sys.argv
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+if argv:
+    lat = lat[np.linspace(0, wl.cells - 1, int(argv[0])).astype(np.int64)]
 C = lat.size
 base = synth.gridded_field(lat, wl.base_axis().dayofyr, seed=1, device="cuda")
 run = synth.gridded_field(lat, wl.run_axis().dayofyr, seed=2, trend=4.0, device="cuda")
 P, D, Y = len(wl.percentiles), len(wl.defs), st.n_years
-h_base = torch.empty(base.shape, dtype=torch.float32, pin_memory=True); h_base.copy_(base)
-h_run = torch.empty(run.shape, dtype=torch.float32, pin_memory=True); h_run.copy_(run)
-h_thr = torch.empty((C, wt.n_doy, P), dtype=torch.float64, pin_memory=True)
-h_out = torch.empty((4, P, D, Y, C), dtype=torch.uint16, pin_memory=True)
+pin = not PAGEABLE
+h_base = torch.empty(base.shape, dtype=torch.float32, pin_memory=pin); h_base.copy_(base)
+h_run = torch.empty(run.shape, dtype=torch.float32, pin_memory=pin); h_run.copy_(run)
+h_thr = torch.empty((C, wt.n_doy, P), dtype=torch.float64, pin_memory=pin)
+h_out = torch.empty((4, P, D, Y, C), dtype=torch.uint16, pin_memory=pin)
+print("host buffers:", "pageable" if PAGEABLE else "pinned", flush=True)
 del base, run
 torch.cuda.empty_cache()
 south = (lat < 0).astype(np.uint8)

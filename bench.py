@@ -333,7 +333,7 @@ def main():
     kernel_ms = {k: float(np.sum(v)) / passes for k, v in by_kernel.items()}
     kernel_launches = {k: len(v) / passes for k, v in by_kernel.items()}
     kernel_share = {k: float(np.sum(v)) / max(sum(np.sum(x) for x in by_kernel.values()), 1e-9) for k, v in by_kernel.items()}
-    thr_kernels = ("k_thr_generic", "k_thr_seg", "k_thr_ranked", "normalize")
+    thr_kernels = ("k_thr_generic", "k_thr_cand", "k_thr_seg", "k_thr_ranked", "normalize")
     alg_bytes = {k: wl.bytes_thresholds(C) for k in thr_kernels}
     alg_bytes.update({"k_hot_words": wl.bytes_metrics(C), "k_scan": wl.bytes_metrics(C)})
     peak, peak_src = peaks()

@@ -632,26 +632,35 @@ __global__ void __launch_bounds__(kSegWarps * 32, 2)
 k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
           const int *__restrict__ seg_time, const int *__restrict__ seg_ne, const uint4 *__restrict__ doy_rng,
           const __grid_constant__ SegGeom geo, const __grid_constant__ SelTable sel, int P, int n, int n_doy,
-          double *__restrict__ out)
+          double *__restrict__ out, const uint32_t *__restrict__ handed_over, int n_blocks)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SelShared s_sel;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // block -> (chunk of cell groups, segment, cell group): blocks in flight share the segment's time rows, and the
-    // halo rows a chunk's neighbouring segments read again are still in L2
-    const int per_chunk = geo.n_seg * geo.gc;
-    const int chunk = blockIdx.x / per_chunk, rem_b = blockIdx.x - chunk * per_chunk;
-    const int gcc = min(geo.gc, geo.n_groups - chunk * geo.gc);   // cell groups of this chunk
-    const int sg = rem_b / gcc, group = chunk * geo.gc + (rem_b - sg * gcc);
-    if (sg >= geo.n_seg) return;                                  // block-uniform (the last chunk is smaller), before any barrier
-    const int64_t c0 = (int64_t)group * kSegWarps;
-    const int NE = seg_ne[sg];
-
     for (int i = tid; i < P; i += kSegWarps * 32) {
         s_sel.pos_lo[i] = sel.pos_lo[i]; s_sel.pos_hi[i] = sel.pos_hi[i]; s_sel.mode[i] = sel.mode[i];
         s_sel.w_lo[i] = sel.w_lo[i]; s_sel.w_hi[i] = sel.w_hi[i];
     }
+    // Work items.  First (only) launch: one per block of the grid.  Second launch behind k_thr_cand (handed_over != nullptr):
+    // the blocks on its hand-over list [count, flags[n_blocks], list[n_blocks]], taken in turns by a small grid; flags[b] = the
+    // warps of block b that k_thr_cand left to this kernel.
+    const bool from_list = handed_over != nullptr;
+    const unsigned n_items = from_list ? handed_over[0] : 1u;
+    for (unsigned item = from_list ? blockIdx.x : 0u; item < n_items; item += from_list ? gridDim.x : 1u) {
+    const unsigned bid = from_list ? handed_over[1 + n_blocks + item] : blockIdx.x;
+    const uint32_t only_mask = from_list ? handed_over[1 + bid] : 0xffffffffu;
+
+    // block -> (chunk of cell groups, segment, cell group): blocks in flight share the segment's time rows, and the
+    // halo rows a chunk's neighbouring segments read again are still in L2
+    const int per_chunk = geo.n_seg * geo.gc;
+    const int chunk = bid / per_chunk, rem_b = bid - chunk * per_chunk;
+    const int gcc = min(geo.gc, geo.n_groups - chunk * geo.gc);   // cell groups of this chunk
+    const int sg = rem_b / gcc, group = chunk * geo.gc + (rem_b - sg * gcc);
+    if (sg >= geo.n_seg) return;                                  // block-uniform (the last chunk is smaller; never on the list), before any barrier
+    const int64_t c0 = (int64_t)group * kSegWarps;
+    const int NE = seg_ne[sg];
+
     // ---- G. gather the [cells x NE] tile: lanes 8j .. 8j+7 read the 8 cells of one time step ----
     {
         const int *st = seg_time + (size_t)sg * kSegCap;
@@ -664,9 +673,10 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_dst + 4u * k), "l"(src + (int64_t)st[k] * ld_t) : "memory");
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
-    __syncthreads();                                              // the only block-wide barrier
+    __syncthreads();                                              // the tile is complete
+    [&]() {                                                       // everything below is warp-private: `return` leaves this warp's item
     const int64_t cell = c0 + warp;
-    if (cell >= C) return;                                        // warp-uniform
+    if (cell >= C || !((only_mask >> warp) & 1u)) return;         // warp-uniform
 
     const uint32_t s_base = smem_u32(smem_raw + (size_t)warp * kSegWarpBytes);
     const uint32_t s_sv = s_base + kSegOffSv, s_cnt = s_base + kSegOffCnt, s_pb = s_cnt, s_rw = s_base + kSegOffRw,
@@ -1055,6 +1065,423 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         dl = dl2 + q_dl; p = p2 + q_p;
         if (p >= P) { p -= P; dl++; }
     }
+    }();
+    if (from_list) __syncthreads();                               // the next item's gather overwrites the tiles
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// k_thr_cand: the register- and shared-memory-light variant of k_thr_seg for the candidate path (high quantiles, finite
+// samples), 24 warps per SM instead of 16 - k_thr_seg is bound by latency at its occupancy.  Phase 1 streams over the tile
+// instead of holding it in 32 registers per lane, the candidates (at most kLCap = 512: 16 rounds) are compacted into their
+// own area, and the dead tile then takes the counters.  A warp whose segment has non-finite samples or more candidates
+// sets its bit in handed_over[block]; k_thr_seg runs behind this kernel for exactly those warps.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kLRounds = 24, kLCap = 32 * kLRounds;
+constexpr int kLOffTile = 0;                                      // f32 [1024] tile -> u32 [1056] counters -> PB [32][33]
+constexpr int kLOffSv = 4224;                                     // f32 [512] candidates, then the sorted values
+constexpr int kLOffRw = kLOffSv + 4 * kLCap;                      // u8 [512] rows | u16 [256] work list | u32 [..] long runs; then cum u16 [32][34]
+constexpr int kLOffWl = kLOffRw + kLCap;
+constexpr int kLOffLong = kLOffWl + kLCap;
+constexpr int kLWarpBytes = kLOffRw + kSegRowsMax * kSegCst * 2 + 16;          // = 16 (mod 128)
+static_assert(kLOffLong + 64 <= kLOffRw + kSegRowsMax * kSegCst * 2, "work areas do not fit under cum");
+static_assert(kLWarpBytes % 128 == 16, "tile rows of the 8 warps must start in different banks");
+
+__global__ void __launch_bounds__(kSegWarps * 32, 3)
+k_thr_cand(const float *__restrict__ temps, int64_t C, int64_t ld_t,
+          const int *__restrict__ seg_time, const int *__restrict__ seg_ne, const uint4 *__restrict__ doy_rng,
+          const __grid_constant__ SegGeom geo, const __grid_constant__ SelTable sel, int P, int n, int n_doy,
+          double *__restrict__ out, uint32_t *__restrict__ handed_over)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SelShared s_sel;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // block -> (chunk of cell groups, segment, cell group): blocks in flight share the segment's time rows, and the
+    // halo rows a chunk's neighbouring segments read again are still in L2
+    const int per_chunk = geo.n_seg * geo.gc;
+    const int chunk = blockIdx.x / per_chunk, rem_b = blockIdx.x - chunk * per_chunk;
+    const int gcc = min(geo.gc, geo.n_groups - chunk * geo.gc);   // cell groups of this chunk
+    const int sg = rem_b / gcc, group = chunk * geo.gc + (rem_b - sg * gcc);
+    if (sg >= geo.n_seg) return;                                  // block-uniform (the last chunk is smaller), before any barrier
+    const int64_t c0 = (int64_t)group * kSegWarps;
+    const int NE = seg_ne[sg];
+
+    for (int i = tid; i < P; i += kSegWarps * 32) {
+        s_sel.pos_lo[i] = sel.pos_lo[i]; s_sel.pos_hi[i] = sel.pos_hi[i]; s_sel.mode[i] = sel.mode[i];
+        s_sel.w_lo[i] = sel.w_lo[i]; s_sel.w_hi[i] = sel.w_hi[i];
+    }
+    // ---- G. gather the [cells x NE] tile: lanes 8j .. 8j+7 read the 8 cells of one time step ----
+    {
+        const int *st = seg_time + (size_t)sg * kSegCap;
+        const int cl = tid & (kSegWarps - 1);
+        const float *src = temps + min(c0 + cl, C - 1);
+        float *dst = (float *)(smem_raw + (size_t)cl * kLWarpBytes + kLOffTile);
+        const uint32_t s_dst = smem_u32(dst);
+#pragma unroll 8
+        for (int k = tid / kSegWarps; k < NE; k += 32)            // asynchronous 4-byte copies: every load of the tile is in flight at once
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_dst + 4u * k), "l"(src + (int64_t)st[k] * ld_t) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();                                              // the only block-wide barrier
+    const int64_t cell = c0 + warp;
+    if (cell >= C) return;                                        // warp-uniform
+
+    const uint32_t s_base = smem_u32(smem_raw + (size_t)warp * kLWarpBytes);
+    const uint32_t s_tile = s_base + kLOffTile, s_sv = s_base + kLOffSv, s_cnt = s_tile, s_pb = s_cnt, s_rw = s_base + kLOffRw,
+                   s_wl = s_base + kLOffWl, s_long = s_base + kLOffLong, s_cum = s_rw;
+
+    // ---- 1. one pass over the tile: maximum, non-finite census (nothing is kept in registers yet) ----
+    const float pinf = __int_as_float(0x7f800000);
+    const bool nonfinite = false;                                 // (segments with NaN / inf samples are handed over)
+    const bool cand = true;
+    const int n_nan = 0, n_pinf = 0, n_ninf = 0;
+    auto hand_over = [&]() {                                      // [count, flags[n_blocks], list[n_blocks]]
+        if (lane == 0 && atomicOr(&handed_over[1 + blockIdx.x], 1u << warp) == 0u)
+            handed_over[1 + gridDim.x + atomicAdd(&handed_over[0], 1u)] = blockIdx.x;
+    };
+    float vmax = -pinf;
+    bool odd = false;
+#pragma unroll 4
+    for (int m = 0; 32 * m < NE; m++) {
+        const float v = lds_f32(s_tile + 4u * (32 * m + lane));
+        const bool valid = 32 * m + lane < NE;
+        odd |= valid && !(fabsf(v) < pinf);
+        if (valid) vmax = fmaxf(vmax, v);
+    }
+    if (__any_sync(0xffffffffu, odd)) { hand_over(); return; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+
+    // ---- 1b. candidate filter (see k_thr_seg): tau = min over rows of the row's cand_m-th largest; candidates = samples >= tau ----
+    float vmin;
+    int NEc;
+    float x[kLRounds];
+    uint32_t rw4[kLRounds / 4];
+    {
+        const int R0 = (NE * geo.ny_magic) >> 16;
+        float tau = pinf;                                         // lane = row
+        if (lane < R0) {
+            const uint32_t a0 = s_tile + 4u * (uint32_t)(lane * geo.n_y);
+            switch (geo.cand_m) {                                 // warp-uniform
+            case 1: tau = seg_row_top<1>(a0, geo.n_y); break;
+            case 2: tau = seg_row_top<2>(a0, geo.n_y); break;
+            case 3: tau = seg_row_top<3>(a0, geo.n_y); break;
+            case 4: tau = seg_row_top<4>(a0, geo.n_y); break;
+            case 5: tau = seg_row_top<5>(a0, geo.n_y); break;
+            case 6: tau = seg_row_top<6>(a0, geo.n_y); break;
+            case 7: tau = seg_row_top<7>(a0, geo.n_y); break;
+            default: tau = seg_row_top<8>(a0, geo.n_y); break;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+        int mine = 0;
+#pragma unroll 4
+        for (int m = 0; 32 * m < NE; m++) mine += (32 * m + lane < NE && lds_f32(s_tile + 4u * (32 * m + lane)) >= tau) ? 1 : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        NEc = __shfl_sync(0xffffffffu, incl, 31);
+        if (NEc > kLCap) { hand_over(); return; }                 // warp-uniform: more candidates than this kernel orders
+        uint32_t pos = (uint32_t)(incl - mine);                   // every lane packs its own candidates behind those of the lanes before it
+#pragma unroll 4
+        for (int m = 0; 32 * m < NE; m++) {
+            const float v = lds_f32(s_tile + 4u * (32 * m + lane));
+            if (32 * m + lane < NE && v >= tau) {
+                sts_f32(s_sv + 4u * pos, v);
+                sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
+                pos++;
+            }
+        }
+        __syncwarp();                                             // the tile is dead: its place takes the counters
+        for (int i = lane; i < 1024 + 32; i += 32) sts_u32(s_cnt + 4u * i, 0u);
+#pragma unroll
+        for (int m = 0; m < kLRounds; m++) {
+            if ((m & 3) == 0) rw4[m >> 2] = 0u;
+            const bool have = NEc - lane > 32 * m;
+            x[m] = have ? lds_f32(s_sv + 4u * (32 * m + lane)) : 0.0f;
+            rw4[m >> 2] |= (have ? lds_u8(s_rw + 32 * m + lane) : 0u) << (8 * (m & 3));
+        }
+        vmin = tau;
+        __syncwarp();
+    }
+
+    // ---- 2. monotone buckets; one atomic claims the slot inside the bucket ----
+    const float range = vmax - vmin;
+    const float scale = (range > 0.0f && range < pinf) ? (float)(kSegNBF - 1) / range : 0.0f;
+    uint32_t pk[kLRounds];                                      // where the counter is | slot
+    int n_wl = 0;                                                 // warp-uniform
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int nl = NEc - lane;                                     // round m holds a sample of this lane iff nl > 32 m
+    if (!nonfinite) {
+#pragma unroll
+        for (int m0 = 0; m0 < kLRounds; m0 += kSegBatch) {
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
+            if (32 * m0 < NEc) seg_claim<false>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
+        }
+    } else {
+#pragma unroll
+        for (int m0 = 0; m0 < kLRounds; m0 += kSegBatch) {
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) pk[m0 + j] = 0u;
+            if (32 * m0 < NEc) seg_claim<true>(x, pk, m0, nl, vmin, scale, s_cnt, s_wl, n_wl, lt_mask);
+        }
+    }
+    __syncwarp();
+
+    // ---- 3. exclusive scan: lane l owns words 32 l .. 32 l + 31 (at 33 l + i); low halves = buckets < 1024 come first ----
+    {
+        const uint32_t a0 = s_cnt + 4u * (33u * lane);
+        uint32_t tot = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; i++) tot += lds_u32(a0 + 4u * i);     // two 16-bit sums per add: neither can carry (<= 1024)
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t carry = (incl - tot) + ((all & 0xffffu) << 16);      // high halves start after every low-half bucket
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const uint32_t wv = lds_u32(a0 + 4u * i);
+            sts_u32(a0 + 4u * i, carry);
+            carry += wv;
+        }
+    }
+    __syncwarp();
+
+    // ---- 4. scatter (value, local row) to the sorted position; exact order inside the work-list buckets ----
+#pragma unroll
+    for (int m0 = 0; m0 < kLRounds; m0 += kSegBatch) {
+        if (32 * m0 < NEc) {                                       // warp-uniform
+            uint32_t bw[kSegBatch];
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) bw[j] = lds_u32(s_cnt + ((pk[m0 + j] >> 9) & ~3u));   // the batch's base lookups overlap
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) {
+                if (nl > 32 * (m0 + j)) {
+                    const uint32_t pos = ((bw[j] >> ((pk[m0 + j] >> 6) & 16u)) & 0xffffu) + (pk[m0 + j] & 1023u);
+                    sts_f32(s_sv + 4u * pos, x[m0 + j]);
+                    const uint32_t row_all = ((uint32_t)(32 * (m0 + j) + lane) * (uint32_t)geo.ny_magic) >> 16;
+                    sts_u8(s_rw + pos, cand ? (rw4[(m0 + j) >> 2] >> (8 * ((m0 + j) & 3))) & 0xffu : row_all);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    {
+        int n_long = 0;
+        for (int q0 = 0; q0 < n_wl; q0 += 32) {
+            const int q = q0 + lane;
+            bool is_long = false;
+            uint32_t desc = 0u;
+            if (q < n_wl) {
+                const uint32_t b = lds_u16(s_wl + 2u * q);
+                const int i0 = seg_bucket_base(s_cnt, b), i1 = seg_bucket_base(s_cnt, b + 1u);
+                if (i1 - i0 > kSegLongRun) { is_long = true; desc = (uint32_t)i0 | ((uint32_t)i1 << 16); }
+                else if (i1 - i0 == 2) {                          // the common case: one compare, maybe one swap
+                    const float v0 = lds_f32(s_sv + 4u * i0), v1 = lds_f32(s_sv + 4u * i0 + 4u);
+                    if (v0 > v1) {
+                        const uint32_t r0 = lds_u8(s_rw + i0), r1 = lds_u8(s_rw + i0 + 1);
+                        sts_f32(s_sv + 4u * i0, v1); sts_f32(s_sv + 4u * i0 + 4u, v0);
+                        sts_u8(s_rw + i0, r1); sts_u8(s_rw + i0 + 1, r0);
+                    }
+                } else {
+                    for (int a = i0 + 1; a < i1; a++) {
+                        const float ka = lds_f32(s_sv + 4u * a);
+                        const uint32_t ra = lds_u8(s_rw + a);
+                        int bpos = a;
+                        while (bpos > i0) {
+                            const float kb = lds_f32(s_sv + 4u * (bpos - 1));
+                            if (kb <= ka) break;
+                            sts_f32(s_sv + 4u * bpos, kb);
+                            sts_u8(s_rw + bpos, lds_u8(s_rw + bpos - 1));
+                            bpos--;
+                        }
+                        sts_f32(s_sv + 4u * bpos, ka);
+                        sts_u8(s_rw + bpos, ra);
+                    }
+                }
+            }
+            const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+            if (is_long) sts_u32(s_long + 4u * (n_long + __popc(lm & ((1u << lane) - 1u))), desc);   // <= 1024 / 33 = 31 long runs
+            n_long += __popc(lm);
+        }
+        __syncwarp();
+        // long runs (ties, fill values, an outlier squeezing the rest into one bucket): nothing to do when already in
+        // order, else a warp-wide counting rank through the (now dead) counter and work-list areas
+        for (int r = 0; r < n_long; r++) {
+            const uint32_t desc = lds_u32(s_long + 4u * r);
+            const int i0 = (int)(desc & 0xffffu), i1 = (int)(desc >> 16), L = i1 - i0;
+            bool bad = false;
+            for (int i = i0 + lane; i + 1 < i1; i += 32) bad |= lds_f32(s_sv + 4u * i) > lds_f32(s_sv + 4u * (i + 1));
+            if (!__any_sync(0xffffffffu, bad)) continue;
+            for (int i = lane; i < L; i += 32) {
+                const float vi = lds_f32(s_sv + 4u * (i0 + i));
+                int rank = 0;
+                for (int j = 0; j < L; j++) {
+                    const float vj = lds_f32(s_sv + 4u * (i0 + j));
+                    rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+                }
+                sts_f32(s_cnt + 4u * rank, vi);
+                sts_u8(s_wl + rank, lds_u8(s_rw + i0 + i));
+            }
+            __syncwarp();
+            for (int i = lane; i < L; i += 32) {
+                sts_f32(s_sv + 4u * (i0 + i), lds_f32(s_cnt + 4u * i));
+                sts_u8(s_rw + i0 + i, lds_u8(s_wl + i));
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    // ---- 5. row bitmaps over the sorted positions -> PB (in place, lane = word) and cum (lane = row) ----
+    const int R = (NE * geo.ny_magic) >> 16;                      // rows of this segment (NE = R * n_y)
+    for (int i = lane; i < kSegRowsMax * kSegPst; i += 32) sts_u32(s_pb + 4u * i, 0u);
+    __syncwarp();
+#pragma unroll
+    for (int m0 = 0; m0 < kLRounds; m0 += kSegBatch) {
+        if (32 * m0 < NEc) {                                       // warp-uniform
+            uint32_t rr[kSegBatch];
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++) rr[j] = lds_u8(s_rw + 32 * (m0 + j) + lane);
+#pragma unroll
+            for (int j = 0; j < kSegBatch; j++)
+                if (nl > 32 * (m0 + j)) reds_or(s_pb + 4u * (rr[j] * kSegPst + (m0 + j)), 1u << lane);
+        }
+    }
+    __syncwarp();
+    {
+        uint32_t acc = 0u;
+        for (int i = 0; i < R; i++) {
+            const uint32_t a = s_pb + 4u * (i * kSegPst + lane), t = lds_u32(a);
+            sts_u32(a, acc);
+            acc |= t;
+        }
+        sts_u32(s_pb + 4u * (R * kSegPst + lane), acc);
+    }
+    __syncwarp();
+    if (lane <= R) {
+        uint32_t run = 0u;
+#pragma unroll 8
+        for (int w = 0; w < 32; w++) {
+            sts_u16(s_cum + 2u * (lane * kSegCst + w), run);
+            run += __popc(lds_u32(s_pb + 4u * (lane * kSegPst + w)));
+        }
+        sts_u16(s_cum + 2u * (lane * kSegCst + 32), run);          // all of them
+    }
+    __syncwarp();
+
+    // ---- 6. queries: one (day of the segment, percentile) per lane, two rounds of 32 queries in flight ----
+    const int L_ninf = n_ninf, L_fin = NE - n_nan - n_pinf, L_pinf = NE - n_nan;   // where the finite / +inf / NaN samples begin
+    const int d0 = sg * geo.S, nd = min(n_doy, d0 + geo.S) - d0;
+    const unsigned char *wbase = smem_raw + (size_t)warp * kLWarpBytes;
+    const float *sv_p = (const float *)(wbase + kLOffSv);
+    const uint32_t *pb_p = (const uint32_t *)(wbase + kLOffTile);
+    const uint16_t *cum_p = (const uint16_t *)(wbase + kLOffRw);
+    double *out_c = out + cell * n_doy * (int64_t)P;
+
+    auto answer = [&](int dl, int p) {
+        const int d = d0 + dl;
+        const uint4 rg = doy_rng[d];
+        const int n1 = (int)byte_of(rg, 0), n2 = (int)byte_of(rg, 1);
+        const int pos_lo = s_sel.pos_lo[p], pos_hi = s_sel.pos_hi[p], mode = s_sel.mode[p];
+        int lr_lo, lr_hi, w_nan = 0, w_pinf = 0, w_ninf = 0;
+        if (n1 == 1 && n2 == 0) {                                 // one contiguous run of rows, each pooled once (almost every day)
+            SegWin<1> win;
+            const uint32_t r0 = byte_of(rg, 2), r1 = byte_of(rg, 5);
+            win.ca[0] = cum_p + r1 * kSegCst; win.cb[0] = cum_p + r0 * kSegCst;
+            win.pa[0] = pb_p + r1 * kSegPst; win.pb[0] = pb_p + r0 * kSegPst;
+            win.n1 = 1; win.nr = 1;
+            const int off = cand ? n - win.before(32) : 0;        // the window's members below tau
+            seg_pick<1>(win, pos_lo - off, pos_hi - off, lr_lo, lr_hi);
+            if (nonfinite) {
+                const int b_pinf = seg_below<1>(win, L_pinf, n);
+                w_ninf = seg_below<1>(win, L_ninf, n);
+                w_pinf = b_pinf - seg_below<1>(win, L_fin, n);
+                w_nan = n - b_pinf;
+            }
+        } else {
+            SegWin<kSegRanges> win;
+            win.n1 = n1; win.nr = n1 + n2;
+#pragma unroll
+            for (int k = 0; k < kSegRanges; k++) {
+                // slot k: k < n1 -> bytes 2+k / 5+k, else the (k - n1)-th pooled-twice range -> bytes 8+.. / 10+..
+                uint32_t r0 = 0u, r1 = 0u;
+#pragma unroll
+                for (int j = 0; j < 3; j++) if (k == j && j < n1) { r0 = byte_of(rg, 2 + j); r1 = byte_of(rg, 5 + j); }
+#pragma unroll
+                for (int j = 0; j < 2; j++) if (k == n1 + j && j < n2) { r0 = byte_of(rg, 8 + j); r1 = byte_of(rg, 10 + j); }
+                win.ca[k] = cum_p + r1 * kSegCst; win.cb[k] = cum_p + r0 * kSegCst;
+                win.pa[k] = pb_p + r1 * kSegPst; win.pb[k] = pb_p + r0 * kSegPst;
+            }
+            const int off = cand ? n - win.before(32) : 0;
+            seg_pick<kSegRanges>(win, pos_lo - off, pos_hi - off, lr_lo, lr_hi);
+            if (nonfinite) {
+                const int b_pinf = seg_below<kSegRanges>(win, L_pinf, n);
+                w_ninf = seg_below<kSegRanges>(win, L_ninf, n);
+                w_pinf = b_pinf - seg_below<kSegRanges>(win, L_fin, n);
+                w_nan = n - b_pinf;
+            }
+        }
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        const double lower = (double)sv_p[lr_lo], upper = (double)sv_p[lr_hi];
+        double v;
+        if (mode == kSelInterp) {                                 // arraymath.py:1697-1701
+            v = __dadd_rn(__dmul_rn(lower, s_sel.w_lo[p]), __dmul_rn(upper, s_sel.w_hi[p]));
+        } else if (mode == kSelMax) {                             // arraymath.py:1669-1675
+            v = upper;
+            if ((w_pinf | w_ninf) && isinf(v)) v = nan;
+        } else {                                                  // arraymath.py:1678-1695
+            v = lower;
+            if (w_pinf | w_ninf) {
+                const int n_fin = n - (w_pinf + w_ninf);
+                if (n_fin == 0) v = nan;
+                if (w_pinf == 1 && n == 2) v = nan;
+                if (w_ninf > 1) v = nan;
+                if (n_fin == 1 && w_pinf > 1 && w_ninf != 1) v = nan;
+            }
+        }
+        if (w_nan > 0) v = nan;                                   // _can_collect_percentiles, arraymath.py:1714
+        out_c[d * P + p] = v;
+    };
+
+    // both queries of a lane on the common path (one run of rows, plain interpolation, finite samples): worked on together
+    auto answer2 = [&](int dl_a, int p_a, int dl_b, int p_b) -> bool {
+        const uint4 rg_a = doy_rng[d0 + dl_a], rg_b = doy_rng[d0 + dl_b];
+        const int lo_a = s_sel.pos_lo[p_a], hi_a = s_sel.pos_hi[p_a], lo_b = s_sel.pos_lo[p_b], hi_b = s_sel.pos_hi[p_b];
+        const bool plain = (rg_a.x & 0xffffu) == 1u && (rg_b.x & 0xffffu) == 1u && s_sel.mode[p_a] == kSelInterp && s_sel.mode[p_b] == kSelInterp &&
+                           hi_a - lo_a <= 1 && hi_b - lo_b <= 1;
+        if (!plain) return false;
+        SegWin<1> wa, wb;
+        const uint32_t r0a = byte_of(rg_a, 2), r1a = byte_of(rg_a, 5), r0b = byte_of(rg_b, 2), r1b = byte_of(rg_b, 5);
+        wa.ca[0] = cum_p + r1a * kSegCst; wa.cb[0] = cum_p + r0a * kSegCst; wa.pa[0] = pb_p + r1a * kSegPst; wa.pb[0] = pb_p + r0a * kSegPst;
+        wb.ca[0] = cum_p + r1b * kSegCst; wb.cb[0] = cum_p + r0b * kSegCst; wb.pa[0] = pb_p + r1b * kSegPst; wb.pb[0] = pb_p + r0b * kSegPst;
+        wa.n1 = wa.nr = wb.n1 = wb.nr = 1;
+        int la, ha, lb, hb;
+        const int off_a = cand ? n - wa.before(32) : 0, off_b = cand ? n - wb.before(32) : 0;
+        seg_pick2(wa, wb, lo_a - off_a, hi_a - off_a, lo_b - off_b, hi_b - off_b, la, ha, lb, hb);
+        out_c[(d0 + dl_a) * P + p_a] = __dadd_rn(__dmul_rn((double)sv_p[la], s_sel.w_lo[p_a]), __dmul_rn((double)sv_p[ha], s_sel.w_hi[p_a]));
+        out_c[(d0 + dl_b) * P + p_b] = __dadd_rn(__dmul_rn((double)sv_p[lb], s_sel.w_lo[p_b]), __dmul_rn((double)sv_p[hb], s_sel.w_hi[p_b]));
+        return true;
+    };
+
+    const int q_dl = 32 / P, q_p = 32 - q_dl * P;                // one round of 32 queries further: q_dl days and q_p percentiles
+    int dl = lane / P, p = lane - dl * P;
+    const int nq = nd * P;
+    for (int qi = lane; qi < nq; qi += 64) {
+        int dl2 = dl + q_dl, p2 = p + q_p;
+        if (p2 >= P) { p2 -= P; dl2++; }
+        const bool two = qi + 32 < nq;
+        if (!(two && !nonfinite && answer2(dl, p, dl2, p2))) {
+            answer(dl, p);
+            if (two) answer(dl2, p2);
+        }
+        dl = dl2 + q_dl; p = p2 + q_p;
+        if (p >= P) { p -= P; dl++; }
+    }
 }
 
 static bool bad_dims(int64_t C, int64_t T_b, int n_doy, int n_y, int W, int P)
@@ -1259,6 +1686,8 @@ struct ThrLayout {
     uint8_t *doy_dup = nullptr;
     int *seg_time = nullptr, *seg_ne = nullptr;      // k_thr_seg tables
     uint8_t *doy_rng = nullptr;
+    uint32_t *handed_over = nullptr;                 // per k_thr_cand block: the warps left to k_thr_seg
+    size_t handed_over_count = 0;
 };
 
 static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_norm, int n_doy, int n_y, int W)
@@ -1274,12 +1703,15 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.seg_time = cv.take<int>((size_t)n_doy * kSegCap);                     // <= n_doy segments
     L.seg_ne = cv.take<int>((size_t)n_doy);
     L.doy_rng = cv.take<uint8_t>((size_t)n_doy * 16);
+    L.handed_over_count = (size_t)(C / kSegWarps + 2 + thr_chunk_groups(T_b)) * (size_t)n_doy;   // >= blocks of the segment kernels
+    L.handed_over = cv.take<uint32_t>(1 + 2 * L.handed_over_count);       // count, flags[blocks], list[blocks]
     L.total = cv.off;
     return L;
 }
 
 static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
 static int g_force_ranked = 0;
+static int g_seg_light = 1;          // test hook: 0 = the candidate path runs in k_thr_seg itself (no k_thr_cand)
 static int g_seg_candidates = 1;     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
 
 // The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
@@ -1367,9 +1799,32 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         const int64_t n_chunks = (geo.n_groups + geo.gc - 1) / geo.gc;
         const int64_t blocks = n_chunks * geo.n_seg * geo.gc;
         if (blocks > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
+        if (geo.cand_m > 0 && g_seg_light && (size_t)blocks <= L.handed_over_count) {
+            // high quantiles: the light kernel first, then k_thr_seg for the warps it handed over (non-finite samples,
+            // more than kLCap candidates), a small grid taking the blocks on the hand-over list in turns
+            static bool light_attr_done = false;
+            const size_t smem_l = (size_t)kSegWarps * kLWarpBytes;
+            if (!light_attr_done) {
+                HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                light_attr_done = true;
+            }
+            HDP_CUDA_TRY(cudaMemsetAsync(L.handed_over, 0, sizeof(uint32_t) * (size_t)(1 + blocks), st));
+            {
+                KernelTimer timer(kThrCand, st);
+                k_thr_cand<<<(unsigned)blocks, kSegWarps * 32, smem_l, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel,
+                                                                          P, (int)b, n_doy, d_out, L.handed_over);
+                HDP_LAUNCH_CHECK();
+            }
+            KernelTimer timer(kThrSeg, st);
+            const unsigned turns = (unsigned)std::min<int64_t>(blocks, 2 * 148 * 4);
+            k_thr_seg<<<turns, kSegWarps * 32, smem, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel, P,
+                                                           (int)b, n_doy, d_out, L.handed_over, (int)blocks);
+            HDP_LAUNCH_CHECK();
+            return HDP_B200_OK;
+        }
         KernelTimer timer(kThrSeg, st);
         k_thr_seg<<<(unsigned)blocks, kSegWarps * 32, smem, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel, P,
-                                                                  (int)b, n_doy, d_out);
+                                                                  (int)b, n_doy, d_out, nullptr, (int)blocks);
         HDP_LAUNCH_CHECK();
         return HDP_B200_OK;
     }
@@ -1409,7 +1864,7 @@ using namespace hdp;
 
 extern "C" {
 
-void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; }
+void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; g_seg_light = on != 4; }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                                            int n_doy, int n_y, int W, int P)

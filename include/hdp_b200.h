@@ -79,8 +79,10 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Test hook: which kernel hdp_b200_thresholds uses.  0 = default (k_thr_seg with its candidate filter where the tables
- * allow, else k_thr_ranked, else k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled
- * any number of times); 2 = k_thr_ranked instead of k_thr_seg; 3 = k_thr_seg without the candidate filter. */
+ * allow - for high quantiles in its light variant k_thr_cand, with k_thr_seg behind it for the warps that one hands over -
+ * else k_thr_ranked, else k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled any
+ * number of times); 2 = k_thr_ranked instead of k_thr_seg; 3 = k_thr_seg without the candidate filter; 4 = k_thr_seg with
+ * the candidate filter but without k_thr_cand. */
 void hdp_b200_thresholds_force_generic(int on);
 
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
@@ -168,6 +170,7 @@ int64_t hdp_b200_launch_count(void);
 #define HDP_B200_KERNEL_THR_SEG      6   /* k_thr_seg */
 #define HDP_B200_KERNEL_THR_RANKED   7   /* k_thr_ranked */
 #define HDP_B200_KERNEL_MEASURE      8   /* k_measure */
+#define HDP_B200_KERNEL_THR_CAND     9   /* k_thr_cand */
 void hdp_b200_timing_enable(int on);
 int  hdp_b200_timing_read(int *ids, float *ms, int cap);
 

@@ -32,12 +32,12 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
-@pytest.fixture(params=["seg", "seg_all", "ranked", "generic"])
+@pytest.fixture(params=["seg", "seg_all", "seg_heavy", "ranked", "generic"])
 def thr_path(request, core):
     """Every threshold path: k_thr_seg with and without its candidate filter, k_thr_ranked, and the generic gather+sort
     fallback."""
     from hdp_b200 import _lib
-    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2, "seg_all": 3}[request.param])
+    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2, "seg_all": 3, "seg_heavy": 4}[request.param])
     yield request.param
     _lib.lib().hdp_b200_thresholds_force_generic(0)
 
@@ -124,6 +124,12 @@ def test_thresholds_high_quantiles_candidate_filter(core, thr_path, calendar, ye
     x[:, 7] = np.where(rng.random(T) < 0.3, 99.0, x[:, 7])    # 30 % fill value above the data: ties inside the top
     x[:, 8] = (np.arange(T) % 7).astype(np.float32)
     x[:, 9] = np.float32(20.0) + np.arange(T, dtype=np.float32) * np.float32(2e-6)
+    # non-finite samples: the light kernel hands these segments over to k_thr_seg (as it does columns 1, 2 and 7, whose
+    # candidates outnumber what it orders)
+    x[rng.integers(0, T, 6), 11] = np.nan
+    x[rng.integers(0, T, 6), 12] = np.inf
+    x[rng.integers(0, T, 6), 13] = -np.inf
+    x[T // 3, 14], x[T // 3 + 1, 14] = np.inf, np.nan
     want = oracle.thresholds_batch(x, wt.window_samples(), q)
     got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
     assert bits_equal(got, want)

@@ -1087,6 +1087,25 @@ constexpr int kLWarpBytes = kLOffRw + kSegRowsMax * kSegCst * 2 + 16;          /
 static_assert(kLOffLong + 64 <= kLOffRw + kSegRowsMax * kSegCst * 2, "work areas do not fit under cum");
 static_assert(kLWarpBytes % 128 == 16, "tile rows of the 8 warps must start in different banks");
 
+// seg_row_top plus the row's maximum (into vmax) and whether the row holds a NaN or an infinity (into odd)
+template <int M>
+__device__ __forceinline__ float seg_row_top_chk(uint32_t a0, int n_y, float &vmax, bool &odd)
+{
+    const float pinf = __int_as_float(0x7f800000);
+    float t[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) t[i] = -pinf;
+#pragma unroll 2
+    for (int y = 0; y < n_y; y++) {
+        float v = lds_f32(a0 + 4u * y);
+        odd |= !(fabsf(v) < pinf);
+#pragma unroll
+        for (int i = 0; i < M; i++) { const float hi = fmaxf(t[i], v); v = fminf(t[i], v); t[i] = hi; }
+    }
+    vmax = t[0];
+    return t[M - 1];
+}
+
 __global__ void __launch_bounds__(kSegWarps * 32, 3)
 k_thr_cand(const float *__restrict__ temps, int64_t C, int64_t ld_t,
           const int *__restrict__ seg_time, const int *__restrict__ seg_ne, const uint4 *__restrict__ doy_rng,
@@ -1131,7 +1150,8 @@ k_thr_cand(const float *__restrict__ temps, int64_t C, int64_t ld_t,
     const uint32_t s_tile = s_base + kLOffTile, s_sv = s_base + kLOffSv, s_cnt = s_tile, s_pb = s_cnt, s_rw = s_base + kLOffRw,
                    s_wl = s_base + kLOffWl, s_long = s_base + kLOffLong, s_cum = s_rw;
 
-    // ---- 1. one pass over the tile: maximum, non-finite census (nothing is kept in registers yet) ----
+    // ---- 1. lanes = rows: the row's cand_m largest samples (tau = the smallest of the rows' cand_m-th largest, the
+    //         maximum = the largest of the rows' largest), non-finite census; nothing is kept in registers yet ----
     const float pinf = __int_as_float(0x7f800000);
     const bool nonfinite = false;                                 // (segments with NaN / inf samples are handed over)
     const bool cand = true;
@@ -1140,60 +1160,52 @@ k_thr_cand(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         if (lane == 0 && atomicOr(&handed_over[1 + blockIdx.x], 1u << warp) == 0u)
             handed_over[1 + gridDim.x + atomicAdd(&handed_over[0], 1u)] = blockIdx.x;
     };
-    float vmax = -pinf;
-    bool odd = false;
-#pragma unroll 4
-    for (int m = 0; 32 * m < NE; m++) {
-        const float v = lds_f32(s_tile + 4u * (32 * m + lane));
-        const bool valid = 32 * m + lane < NE;
-        odd |= valid && !(fabsf(v) < pinf);
-        if (valid) vmax = fmaxf(vmax, v);
-    }
-    if (__any_sync(0xffffffffu, odd)) { hand_over(); return; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-
-    // ---- 1b. candidate filter (see k_thr_seg): tau = min over rows of the row's cand_m-th largest; candidates = samples >= tau ----
-    float vmin;
+    float vmax = -pinf, vmin;
     int NEc;
     float x[kLRounds];
     uint32_t rw4[kLRounds / 4];
     {
         const int R0 = (NE * geo.ny_magic) >> 16;
-        float tau = pinf;                                         // lane = row
+        float tau = pinf;
+        bool odd = false;
         if (lane < R0) {
             const uint32_t a0 = s_tile + 4u * (uint32_t)(lane * geo.n_y);
             switch (geo.cand_m) {                                 // warp-uniform
-            case 1: tau = seg_row_top<1>(a0, geo.n_y); break;
-            case 2: tau = seg_row_top<2>(a0, geo.n_y); break;
-            case 3: tau = seg_row_top<3>(a0, geo.n_y); break;
-            case 4: tau = seg_row_top<4>(a0, geo.n_y); break;
-            case 5: tau = seg_row_top<5>(a0, geo.n_y); break;
-            case 6: tau = seg_row_top<6>(a0, geo.n_y); break;
-            case 7: tau = seg_row_top<7>(a0, geo.n_y); break;
-            default: tau = seg_row_top<8>(a0, geo.n_y); break;
+            case 1: tau = seg_row_top_chk<1>(a0, geo.n_y, vmax, odd); break;
+            case 2: tau = seg_row_top_chk<2>(a0, geo.n_y, vmax, odd); break;
+            case 3: tau = seg_row_top_chk<3>(a0, geo.n_y, vmax, odd); break;
+            case 4: tau = seg_row_top_chk<4>(a0, geo.n_y, vmax, odd); break;
+            case 5: tau = seg_row_top_chk<5>(a0, geo.n_y, vmax, odd); break;
+            case 6: tau = seg_row_top_chk<6>(a0, geo.n_y, vmax, odd); break;
+            case 7: tau = seg_row_top_chk<7>(a0, geo.n_y, vmax, odd); break;
+            default: tau = seg_row_top_chk<8>(a0, geo.n_y, vmax, odd); break;
             }
         }
+        if (__any_sync(0xffffffffu, odd)) { hand_over(); return; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-        int mine = 0;
-#pragma unroll 4
-        for (int m = 0; 32 * m < NE; m++) mine += (32 * m + lane < NE && lds_f32(s_tile + 4u * (32 * m + lane)) >= tau) ? 1 : 0;
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        NEc = __shfl_sync(0xffffffffu, incl, 31);
-        if (NEc > kLCap) { hand_over(); return; }                 // warp-uniform: more candidates than this kernel orders
-        uint32_t pos = (uint32_t)(incl - mine);                   // every lane packs its own candidates behind those of the lanes before it
+        for (int o = 16; o > 0; o >>= 1) {
+            tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+
+        // ---- 1b. candidate filter (see k_thr_seg): the samples >= tau, packed in tile order into their own area ----
+        int base = 0;
+        const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 4
         for (int m = 0; 32 * m < NE; m++) {
             const float v = lds_f32(s_tile + 4u * (32 * m + lane));
-            if (32 * m + lane < NE && v >= tau) {
+            const bool keep = 32 * m + lane < NE && v >= tau;
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            const uint32_t pos = (uint32_t)base + __popc(bal & lt);
+            if (keep && pos < (uint32_t)kLCap) {
                 sts_f32(s_sv + 4u * pos, v);
                 sts_u8(s_rw + pos, ((uint32_t)(32 * m + lane) * (uint32_t)geo.ny_magic) >> 16);
-                pos++;
             }
+            base += __popc(bal);
         }
+        NEc = base;
+        if (NEc > kLCap) { hand_over(); return; }                 // warp-uniform: more candidates than this kernel orders
+        vmin = tau;
         __syncwarp();                                             // the tile is dead: its place takes the counters
         for (int i = lane; i < 1024 + 32; i += 32) sts_u32(s_cnt + 4u * i, 0u);
 #pragma unroll
@@ -1203,7 +1215,6 @@ k_thr_cand(const float *__restrict__ temps, int64_t C, int64_t ld_t,
             x[m] = have ? lds_f32(s_sv + 4u * (32 * m + lane)) : 0.0f;
             rw4[m >> 2] |= (have ? lds_u8(s_rw + 32 * m + lane) : 0u) << (8 * (m & 3));
         }
-        vmin = tau;
         __syncwarp();
     }
 

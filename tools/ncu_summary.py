@@ -45,8 +45,8 @@ want = [("gpu__time_duration.sum", "duration"), ("smsp__inst_executed.sum", "war
 unit_scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 traffic = {}
 md = [f"# {tag}: `ncu --set full --clock-control none --import-source on`, first launch of each kernel, full cmip6_1deg grid (64 800 cells)\n",
-      "Reports: gpurun_out/prof_%s_{seg,hot,scan}.ncu-rep (not tracked); numbers copied from `ncu -i ... --page raw --csv`.\n" % tag]
-for short in ("seg", "hot", "scan"):
+      "Reports: gpurun_out/prof_%s_{cand,hot,scan}.ncu-rep (not tracked); numbers copied from `ncu -i ... --page raw --csv`.\n" % tag]
+for short in ("cand", "seg", "hot", "scan"):
     rep = os.path.join(out, f"prof_{tag}_{short}.ncu-rep")
     if not os.path.exists(rep):
         continue

@@ -10,6 +10,14 @@
 //     rank = 1 + (n-1) * ((q*100)/100);  f = floor(rank);  m = rank - f
 //     val  = sorted[f-1] * (1-m) + sorted[f] * m
 // which is bit-identical to the reference (tests/test_gpu_parity.py compares at 0 ulp).
+//
+// Kernels, fastest first (hdp_b200_thresholds picks by what the window tables and the quantiles allow):
+//   k_thr_cand     high quantiles, finite samples: a segment of days shares one ordering of the few samples that can be
+//                  among any window's largest (candidate filter); register-light, 24 warps per SM
+//   k_thr_seg      any quantiles, any samples: the same segment scheme over all samples (with the candidate filter when the
+//                  quantiles allow); also works through the segments k_thr_cand hands over
+//   k_thr_ranked   windows that do not fit a segment (31-day windows): one ordering per cell, sliding rank bitmaps
+//   k_thr_generic  any table (rows pooled any number of times, windows of up to 32 768 samples): gather + bitonic sort
 #include <math.h>
 #include <stdlib.h>
 #include <vector>

@@ -182,7 +182,6 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
     from hdp_b200 import workloads, synth
     wl = workloads.get(args.workload)
     cores = host_cores()

@@ -283,7 +283,9 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                     out[o] = (uint16_t)f;
                     out[o + plane] = (uint16_t)nn;
                     out[o + 2 * plane] = (uint16_t)((hwdg[j] >> (BITS * h)) & LANE_MASK);
-                    out[o + 3 * plane] = (uint16_t)(nn ? f / nn : 0u);       // trunc(mean), metric.py:340
+                    // trunc(mean) = f / nn in integers, metric.py:340.  f, nn < 65536, so (f + 0.5) / nn is at least 0.5 / nn
+                    // away from every integer - orders of magnitude more than the error of the fast float division
+                    out[o + 3 * plane] = (uint16_t)(nn ? __float2uint_rz(__fdividef((float)f + 0.5f, (float)nn)) : 0u);
                 }
             }
             cntg[j] = 0u; hwfg[j] = 0u; hwng[j] = 0u; hwdg[j] = 0u;

@@ -1722,7 +1722,9 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.seg_time = cv.take<int>((size_t)n_doy * kSegCap);                     // <= n_doy segments
     L.seg_ne = cv.take<int>((size_t)n_doy);
     L.doy_rng = cv.take<uint8_t>((size_t)n_doy * 16);
-    L.handed_over_count = (size_t)(C / kSegWarps + 2 + thr_chunk_groups(T_b)) * (size_t)n_doy;   // >= blocks of the segment kernels
+    // >= blocks of the segment kernels: a usable segment has 2 S >= W - 1 days (plan_seg), so there are at most n_doy / S_min
+    const int s_min = std::max(1, W / 2);
+    L.handed_over_count = (size_t)(C / kSegWarps + 2 + thr_chunk_groups(T_b)) * (size_t)((n_doy + s_min - 1) / s_min);
     L.handed_over = cv.take<uint32_t>(1 + 2 * L.handed_over_count);       // count, flags[blocks], list[blocks]
     L.total = cv.off;
     return L;

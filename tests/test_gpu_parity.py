@@ -135,6 +135,28 @@ def test_thresholds_high_quantiles_candidate_filter(core, thr_path, calendar, ye
     assert bits_equal(got, want)
 
 
+def test_thresholds_many_handed_over_segments(core):
+    # high quantiles on a grid where every other cell has a NaN / an infinity somewhere and a few are constant: thousands of
+    # (cell, segment) pairs go from k_thr_cand onto the hand-over list, more than the small k_thr_seg grid behind it has blocks
+    # (every block takes several turns); the rest stays on the light kernel
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(61)
+    ax = tb.TimeAxis.date_range("1961-01-01", "1990-12-31", "noleap")
+    wt = tb.window_tables(ax.dayofyr, 7)
+    T, C = len(ax), 12000
+    x = (15 + 12 * np.sin(2 * np.pi * (ax.dayofyr[:, None] - 110) / 365) + 3 * rng.standard_normal((T, C), dtype=np.float32)).astype(np.float32)
+    bad = np.arange(0, C, 2)
+    x[rng.integers(0, T, bad.size), bad] = np.where(rng.random(bad.size) < 0.5, np.nan, np.inf).astype(np.float32)
+    x[:, 5::97] = 3.25
+    q = np.arange(0.9, 1.0, 0.01)
+    got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
+    sel = np.unique(np.concatenate([np.arange(0, 64), rng.integers(0, C, 192), [C - 1]]))
+    want = oracle.thresholds_batch(np.ascontiguousarray(x[:, sel]), wt.window_samples(), q)
+    assert bits_equal(got[sel], want)
+    # NaN rows exactly where a window holds the cell's NaN; every cell without one is finite
+    assert np.isfinite(got[1::2]).all()
+
+
 def test_thresholds_errors(core):
     from hdp_b200 import _tables as tb, _lib
     ax = tb.TimeAxis.daily((1961, 1, 1), 2 * 365, "noleap")

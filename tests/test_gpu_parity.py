@@ -509,3 +509,31 @@ def test_measure_prepass_full_size_throughput(core, capsys):
     assert np.array_equal(_bits32(out[idx].cpu().numpy()), _bits32(want))
     with capsys.disabled():
         print(f"\n[k_measure] {n} elements, {ms:.2f} ms, {12 * n / ms / 1e6:.0f} GB/s (12 B per element)")
+
+
+def test_host_pipeline_pageable_memory_many_ring_blocks(core):
+    # ordinary (pageable) NumPy arrays large enough that every copy runs through several 32 MB blocks of the pinned staging
+    # rings: pitched sample rows, threshold chunks that are one contiguous row longer than a block, pitched result rows;
+    # both host layouts; against the device-resident path bit for bit
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(77)
+    base_ax = tb.TimeAxis.date_range("1961-01-01", "1964-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2007-12-31", "noleap")
+    wt = tb.window_tables(base_ax.dayofyr, 7)
+    C = 40001
+    season = lambda ax: 15 + 10 * np.sin(2 * np.pi * (ax.dayofyr[:, None] - 110) / 365)
+    xb = (season(base_ax) + 3 * rng.standard_normal((len(base_ax), C), dtype=np.float32)).astype(np.float32)
+    xr_ = (season(run_ax) + 2 + 3 * rng.standard_normal((len(run_ax), C), dtype=np.float32)).astype(np.float32)
+    q = np.array([0.5, 0.8, 0.9, 0.95, 0.975, 0.99])
+    thr_d = core.thresholds_array(dev(xb), wt, q)
+    thr_h = core.thresholds_host(xb, wt, q)                                  # 58 MB in, 700 MB out
+    assert bits_equal(thr_h, thr_d.cpu().numpy())
+    st = tb.hemisphere_ranges(run_ax)
+    defs = [[a, b, c] for a in (3, 4) for b in (0, 1) for c in (0, 1)]
+    is_south = (rng.random(C) < 0.5).astype(np.uint8)
+    args = (tb.doy_map(run_ax.dayofyr), defs, st.north, st.south, is_south)
+    out_d = core.metrics_array(dev(xr_), thr_d, *args).cpu().numpy()
+    assert np.array_equal(core.metrics_host(xr_, thr_h, *args), out_d)       # 409 MB + 700 MB in, 107 MB out
+    xr_t = np.ascontiguousarray(xr_.T).T                                     # time-contiguous host layout
+    assert np.array_equal(core.metrics_host(xr_t, thr_h, *args), out_d)
+    core.host_release()

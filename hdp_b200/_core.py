@@ -234,40 +234,101 @@ def _host_measure(x: np.ndarray, name: str):
     if x.dtype != np.float32 or x.ndim != 2:
         raise TypeError(f"{name} must be a 2-D float32 array [T, C]")
     T, C = x.shape
+    if any(s % 4 for s in x.strides):                   # not a whole number of elements (views of packed records)
+        x = np.ascontiguousarray(x)
     ld_t = x.strides[0] // 4 if T > 1 else max(C, 1)
     ld_c = x.strides[1] // 4 if C > 1 else 1
-    if ld_c != 1 and ld_t != 1:
+    if ld_t <= 0 or ld_c <= 0 or (ld_c != 1 and ld_t != 1):   # reversed / broadcast / doubly strided views: one dense copy
         x = np.ascontiguousarray(x)
-        ld_t, ld_c = C, 1
+        ld_t, ld_c = max(C, 1), 1
     return x, int(ld_t), int(ld_c)
 
 
-def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequence[float], out: Optional[np.ndarray] = None) -> np.ndarray:
-    _torch()
+# Device-resident copies of thresholds this process computed, so that the reference workflow compute_thresholds ->
+# compute_group_metrics does not send them back over PCIe.  Keyed by the identity of the host array the library itself
+# allocated and returned READ-ONLY (nobody can change its contents behind the cache; a writable copy is a different
+# array and misses); the entry dies with the array.  Bounded: oldest entries go first.
+_resident = {}                       # id(ndarray) -> (weakref, data pointer, shape, device tensor)
+RESIDENT_BYTES_MAX = 24 << 30
+
+
+def _resident_put(host: np.ndarray, dev) -> None:
+    import weakref
+    key = id(host)
+    _resident[key] = (weakref.ref(host, lambda _r, k=key: _resident.pop(k, None)), host.ctypes.data, host.shape, dev)
+    total = sum(e[3].numel() * 8 for e in _resident.values())
+    for k in list(_resident):
+        if total <= RESIDENT_BYTES_MAX or k == key:
+            continue
+        total -= _resident[k][3].numel() * 8
+        del _resident[k]
+
+
+def resident_thresholds(thr: np.ndarray):
+    """The device copy of ``thr`` if ``thr`` is (a same-shape contiguous view of) an array :func:`thresholds_host` returned."""
+    root = thr
+    while isinstance(getattr(root, "base", None), np.ndarray):
+        root = root.base
+    e = _resident.get(id(root))
+    if e is None or e[0]() is not root or root.flags.writeable:
+        return None
+    if thr.ctypes.data != e[1] or tuple(thr.shape) != tuple(e[2]) or not thr.flags.c_contiguous:
+        return None
+    return e[3]
+
+
+def release_resident() -> None:
+    _resident.clear()
+
+
+def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequence[float], out: Optional[np.ndarray] = None,
+                    keep=None) -> np.ndarray:
+    """Host arrays in, host array out (chunked copy/compute pipeline inside the library).  ``keep``: a float64 CUDA tensor
+    ``[C, n_doy, P]`` that also receives the thresholds, or True to let the library allocate one and remember it for the
+    metric pass (the returned array is then read-only, see :func:`resident_thresholds`)."""
+    torch = _torch()
     L = _lib.lib()
     temps, ld_t, ld_c = _host_measure(temps, "temps")
     T_b, C = temps.shape
     q = np.ascontiguousarray(percentiles, dtype=np.float64).ravel()
     ti, wr = _i32(tables.time_index), _i32(tables.win_rows)
+    remember = keep is True and out is None
+    if keep is True:
+        keep = torch.empty((C, tables.n_doy, q.size), dtype=torch.float64, device="cuda") if remember else None
+    if keep is not None and not (keep.is_cuda and keep.dtype == torch.float64 and keep.is_contiguous()
+                                 and tuple(keep.shape) == (C, tables.n_doy, q.size)):
+        raise TypeError("keep must be a contiguous float64 CUDA tensor [C, n_doy, P]")
     if out is None:
         out = np.empty((C, tables.n_doy, q.size), np.float64)
     assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (C, tables.n_doy, q.size)
     rc = L.hdp_b200_thresholds_host(_hp(temps), C, T_b, ld_t, ld_c, _hp(ti), _hp(wr), tables.n_doy, tables.n_y,
-                                    tables.width, _hp(q), int(q.size), _hp(out))
+                                    tables.width, _hp(q), int(q.size), _hp(out), keep.data_ptr() if keep is not None else None)
     _lib.check(rc, "hdp_b200_thresholds_host")
+    if remember:
+        out.flags.writeable = False
+        _resident_put(out, keep)
     return out
 
 
-def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, season_north, season_south,
+def metrics_host(measure: np.ndarray, thresholds, doy_map, defs, season_north, season_south,
                  is_south=None, out: Optional[np.ndarray] = None) -> np.ndarray:
-    _torch()
+    """``thresholds``: float64 ``[C, n_doy, P]`` as a host array, or as a CUDA tensor (device-resident: no upload).  A host
+    array that :func:`thresholds_host` returned with ``keep=True`` is recognised and its device copy used."""
+    torch = _torch()
     L = _lib.lib()
     measure, ld_t, ld_c = _host_measure(measure, "measure")
     T, C = measure.shape
-    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
-    if thr.ndim != 3 or thr.shape[0] != C:
-        raise TypeError("thresholds must be float64 [C, n_doy, P]")
-    n_doy, P = thr.shape[1], thr.shape[2]
+    d_thr = None
+    if isinstance(thresholds, torch.Tensor):
+        _check_thr(thresholds, C)
+        d_thr, thr = thresholds, None
+        n_doy, P = int(d_thr.shape[1]), int(d_thr.shape[2])
+    else:
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        if thr.ndim != 3 or thr.shape[0] != C:
+            raise TypeError("thresholds must be float64 [C, n_doy, P]")
+        n_doy, P = thr.shape[1], thr.shape[2]
+        d_thr = resident_thresholds(thr)
     dm, df, sn, ss = _metric_tables(doy_map, defs, season_north, season_south)
     if dm.size != T:
         raise ValueError("doy_map must have one entry per time step")
@@ -276,7 +337,8 @@ def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, sea
     if out is None:
         out = np.empty((4, P, D, Y, C), np.uint16)
     assert out.flags.c_contiguous and out.dtype == np.uint16 and out.shape == (4, P, D, Y, C)
-    rc = L.hdp_b200_metrics_host(_hp(measure), C, T, ld_t, ld_c, _hp(thr), n_doy, P, _hp(dm), _hp(df), D, _hp(sn), _hp(ss), Y,
+    rc = L.hdp_b200_metrics_host(_hp(measure), C, T, ld_t, ld_c, _hp(thr) if thr is not None else None,
+                                 d_thr.data_ptr() if d_thr is not None else None, n_doy, P, _hp(dm), _hp(df), D, _hp(sn), _hp(ss), Y,
                                  _hp(south) if south is not None else None, _hp(out))
     _lib.check(rc, "hdp_b200_metrics_host")
     return out
@@ -284,6 +346,7 @@ def metrics_host(measure: np.ndarray, thresholds: np.ndarray, doy_map, defs, sea
 
 def host_release() -> None:
     """Free the streams and device buffers the ``*_host`` entry points keep between calls."""
+    release_resident()
     _lib.lib().hdp_b200_host_release()
 
 

@@ -16,15 +16,17 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libhdp_b200.so")
-SOURCES = ["abi.cu", "threshold.cu", "metric.cu", "measure.cu", "host.cu"]
+SOURCES = ["abi.cu", "threshold.cu", "thr_net.cu", "metric.cu", "measure.cu", "host.cu"]
+HEADERS = ["common.cuh", "thr_net_gen.cuh"]
+OBJ = os.path.join(HERE, "_obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",                 # the f64 interpolation must stay separately rounded (bit-exact parity)
     "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=default",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def nvcc() -> str:
@@ -38,26 +40,48 @@ def sources() -> list:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+def _common_deps() -> list:
+    return [os.path.join(CSRC, h) for h in HEADERS if os.path.exists(os.path.join(CSRC, h))] + [os.path.join(INCLUDE, "hdp_b200.h"), __file__]
+
+
+def _obj_of(src: str) -> str:
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target: str, deps: list) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
-        return False
-    t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "hdp_b200.h"), __file__]
-    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+    return not _stale(LIB, sources() + _common_deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
-        return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", LIB + ".tmp", *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
+def _run(cmd: list, verbose: bool) -> None:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
+        print(" ".join(cmd))
         print(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per source (compiled in parallel, only what changed), then one link: an edit of one kernel file does
+    not recompile the others."""
+    if not force and up_to_date():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ, exist_ok=True)
+    common = _common_deps()
+    todo = [s for s in sources() if force or _stale(_obj_of(s), [s] + common)]
+    extra = ["-Xptxas=-v"] if verbose else []
+    cmds = [[nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", "-o", _obj_of(s), s] for s in todo]
+    with ThreadPoolExecutor(max(1, min(len(cmds), os.cpu_count() or 1))) as pool:
+        list(pool.map(lambda c: _run(c, verbose), cmds))
+    _run([nvcc(), *LINK_FLAGS, "-o", LIB + ".tmp", *[_obj_of(s) for s in sources()]], verbose)
     os.replace(LIB + ".tmp", LIB)
     return LIB
 

@@ -1,4 +1,5 @@
 // abi.cu - library-level entry points and the layout-normalising copy.
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -6,30 +7,30 @@
 
 namespace hdp {
 
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 // ---- per-kernel timing: event pairs recorded on the launching stream, read back on request ----
 struct TimedLaunch { int id; cudaEvent_t start, stop; };
-static bool g_timing = false;
+static std::atomic<bool> g_timing{false};
 static std::vector<TimedLaunch> g_timed;
 static std::mutex g_timed_mu;
 
-KernelTimer::KernelTimer(int id, cudaStream_t s) : on(g_timing), st(s), slot(-1)
+// The timer owns its two events until the launch is bracketed; only complete pairs enter the list that
+// hdp_b200_timing_read drains (a concurrent read can never see, or invalidate, a half-recorded launch).
+KernelTimer::KernelTimer(int id_, cudaStream_t s) : on(g_timing.load(std::memory_order_relaxed)), st(s), id(id_), start(nullptr), stop(nullptr)
 {
     if (!on) return;
-    TimedLaunch t{id, nullptr, nullptr};
-    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) { on = false; return; }
-    cudaEventRecord(t.start, st);
-    std::lock_guard<std::mutex> lk(g_timed_mu);
-    slot = (int)g_timed.size();
-    g_timed.push_back(t);
+    if (cudaEventCreate(&start) != cudaSuccess) { on = false; return; }
+    if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start); on = false; return; }
+    cudaEventRecord(start, st);
 }
 
 KernelTimer::~KernelTimer()
 {
     if (!on) return;
+    cudaEventRecord(stop, st);
     std::lock_guard<std::mutex> lk(g_timed_mu);
-    cudaEventRecord(g_timed[slot].stop, st);
+    g_timed.push_back(TimedLaunch{id, start, stop});
 }
 
 // [C, T] (time-contiguous, ld_t == 1) -> [T, C]: 32x32 tiles through shared memory so that both the
@@ -86,26 +87,28 @@ extern "C" {
 
 int hdp_b200_abi_version(void) { return HDP_B200_ABI_VERSION; }
 
-int64_t hdp_b200_launch_count(void) { return hdp::g_launch_count; }
+int64_t hdp_b200_launch_count(void) { return hdp::g_launch_count.load(std::memory_order_relaxed); }
 
 void hdp_b200_timing_enable(int on)
 {
-    std::lock_guard<std::mutex> lk(hdp::g_timed_mu);
-    hdp::g_timing = on != 0;
+    hdp::g_timing.store(on != 0);
 }
 
 int hdp_b200_timing_read(int *ids, float *ms, int cap)
 {
-    std::lock_guard<std::mutex> lk(hdp::g_timed_mu);
+    std::vector<hdp::TimedLaunch> done;
+    {
+        std::lock_guard<std::mutex> lk(hdp::g_timed_mu);
+        done.swap(hdp::g_timed);
+    }
     int n = 0;
-    for (auto &t : hdp::g_timed) {
+    for (auto &t : done) {
         float v = -1.0f;
         if (cudaEventSynchronize(t.stop) == cudaSuccess) cudaEventElapsedTime(&v, t.start, t.stop);
         if (n < cap) { if (ids) ids[n] = t.id; if (ms) ms[n] = v; n++; }
         cudaEventDestroy(t.start);
         cudaEventDestroy(t.stop);
     }
-    hdp::g_timed.clear();
     return n;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -10,7 +11,7 @@
 namespace hdp {
 
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? HDP_B200_OK : (int)e; }
 
@@ -23,7 +24,7 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? HDP_B200_OK : 
 // After every launch: count it and surface launch-configuration errors without synchronising.
 #define HDP_LAUNCH_CHECK()                                   \
     do {                                                     \
-        ::hdp::g_launch_count++;                             \
+        ::hdp::g_launch_count.fetch_add(1, std::memory_order_relaxed);                             \
         cudaError_t _e = cudaGetLastError();                 \
         if (_e != cudaSuccess) return (int)_e;               \
     } while (0)
@@ -33,7 +34,8 @@ enum KernelId { kNormalize = 1, kThrGeneric = 2, kHotWords = 3, kScan = 4, kUnpa
 struct KernelTimer {
     bool on;
     cudaStream_t st;
-    int slot;
+    int id;
+    cudaEvent_t start, stop;
     KernelTimer(int id, cudaStream_t st);
     ~KernelTimer();
 };

@@ -343,11 +343,12 @@ void hdp_b200_host_release(void)
 
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
-                             const double *h_q, int P, double *h_out)
+                             const double *h_q, int P, double *h_out, double *d_keep)
 {
     if (C < 0 || T_b <= 0 || n_doy <= 0 || n_y <= 0 || W <= 0 || P <= 0) return HDP_B200_ERR_INVALID;
     if (C == 0) return HDP_B200_OK;
     if (!h_temps || !h_out) return HDP_B200_ERR_INVALID;
+    if (ld_t <= 0 || ld_c <= 0) return HDP_B200_ERR_INVALID;              // pitches become size_t below: no reversed views
     if (ld_c != 1 && ld_t != 1) return HDP_B200_ERR_UNSUPPORTED;
     HostCtx *ctx = nullptr;
     int rc = current_ctx(&ctx);
@@ -362,7 +363,7 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
     if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
     for (int i = 0; i < kSlots; i++) {
         if ((rc = ctx->x[i].reserve((size_t)chunk * T_b * sizeof(float)))) return rc;
-        if ((rc = ctx->out[i].reserve((size_t)chunk * out_per_cell))) return rc;
+        if (!d_keep && (rc = ctx->out[i].reserve((size_t)chunk * out_per_cell))) return rc;
     }
     const bool page_in = is_pageable(h_temps), page_out = is_pageable(h_out);
     int64_t i = 0;
@@ -375,14 +376,17 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
         HDP_HOST_TRY(upload_cells(ctx, h_temps, page_in, T_b, ld_t, ld_c, c0, nc, (float *)ctx->x[slot].p, &a, &b, ctx->s_in));
         HDP_HOST_CUDA(cudaEventRecord(ctx->in_ready[slot], ctx->s_in));
         // stage 2: kernels (the slot's previous results must have left for the host)
+        // with d_keep the kernels write the chunk straight into its place in the caller's device-resident copy (which then feeds
+        // hdp_b200_metrics_host without coming back over PCIe) and the D2H copy reads it from there: no slot to wait for
+        double *d_chunk_out = d_keep ? d_keep + (size_t)c0 * n_doy * P : (double *)ctx->out[slot].p;
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_ready[slot], 0));
-        HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
+        if (!d_keep) HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
         HDP_HOST_TRY(thresholds_launch((const float *)ctx->x[slot].p, nc, T_b, a, b, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P,
-                                       (double *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
+                                       d_chunk_out, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
         HDP_HOST_CUDA(cudaEventRecord(ctx->k_done[slot], ctx->s_k));
         // stage 3: results
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[slot], 0));
-        HDP_HOST_TRY(ctx->d2h((char *)(h_out + (size_t)c0 * n_doy * P), 0, (const char *)ctx->out[slot].p, 0, (size_t)nc * out_per_cell, 1,
+        HDP_HOST_TRY(ctx->d2h((char *)(h_out + (size_t)c0 * n_doy * P), 0, (const char *)d_chunk_out, 0, (size_t)nc * out_per_cell, 1,
                               page_out, ctx->s_out));
         HDP_HOST_CUDA(cudaEventRecord(ctx->out_done[slot], ctx->s_out));
     }
@@ -390,14 +394,15 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
 }
 
 int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                          const double *h_thr, int n_doy, int P, const int32_t *h_doy_map,
+                          const double *h_thr, const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
                           const int32_t *h_defs, int D,
                           const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                           const uint8_t *h_is_south, uint16_t *h_out)
 {
     if (C < 0 || T <= 0 || n_doy <= 0 || P <= 0 || D <= 0 || Y < 0 || !h_doy_map) return HDP_B200_ERR_INVALID;
     if (C == 0 || Y == 0) return HDP_B200_OK;
-    if (!h_measure || !h_thr || !h_out) return HDP_B200_ERR_INVALID;
+    if (!h_measure || (!h_thr && !d_thr) || !h_out) return HDP_B200_ERR_INVALID;
+    if (ld_t <= 0 || ld_c <= 0) return HDP_B200_ERR_INVALID;
     if (ld_c != 1 && ld_t != 1) return HDP_B200_ERR_UNSUPPORTED;
     HostCtx *ctx = nullptr;
     int rc = current_ctx(&ctx);
@@ -413,11 +418,11 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
     if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
     for (int i = 0; i < kSlots; i++) {
         if ((rc = ctx->x[i].reserve((size_t)chunk * T * sizeof(float)))) return rc;
-        if ((rc = ctx->aux[i].reserve((size_t)chunk * thr_per_cell))) return rc;
+        if (!d_thr && (rc = ctx->aux[i].reserve((size_t)chunk * thr_per_cell))) return rc;
         if ((rc = ctx->south[i].reserve((size_t)chunk))) return rc;
         if ((rc = ctx->out[i].reserve(rows * chunk * sizeof(uint16_t)))) return rc;
     }
-    const bool page_x = is_pageable(h_measure), page_thr = is_pageable(h_thr), page_out = is_pageable(h_out);
+    const bool page_x = is_pageable(h_measure), page_thr = !d_thr && is_pageable(h_thr), page_out = is_pageable(h_out);
     const bool page_south = h_is_south && is_pageable(h_is_south);
     int64_t i = 0;
     for (int64_t c0 = 0; c0 < C; c0 += chunk, i++) {
@@ -426,15 +431,17 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
         int64_t a, b;
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->k_done[slot], 0));
         HDP_HOST_TRY(upload_cells(ctx, h_measure, page_x, T, ld_t, ld_c, c0, nc, (float *)ctx->x[slot].p, &a, &b, ctx->s_in));
-        HDP_HOST_TRY(ctx->h2d((char *)ctx->aux[slot].p, 0, (const char *)(h_thr + (size_t)c0 * n_doy * P), 0, (size_t)nc * thr_per_cell, 1,
-                              page_thr, ctx->s_in));
+        if (!d_thr)                                                            // device-resident thresholds never cross PCIe again
+            HDP_HOST_TRY(ctx->h2d((char *)ctx->aux[slot].p, 0, (const char *)(h_thr + (size_t)c0 * n_doy * P), 0, (size_t)nc * thr_per_cell, 1,
+                                  page_thr, ctx->s_in));
         if (h_is_south)
             HDP_HOST_TRY(ctx->h2d((char *)ctx->south[slot].p, 0, (const char *)(h_is_south + c0), 0, (size_t)nc, 1, page_south, ctx->s_in));
         HDP_HOST_CUDA(cudaEventRecord(ctx->in_ready[slot], ctx->s_in));
 
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_ready[slot], 0));
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
-        HDP_HOST_TRY(metrics_launch((const float *)ctx->x[slot].p, nc, T, a, b, (const double *)ctx->aux[slot].p, n_doy, P, h_doy_map,
+        HDP_HOST_TRY(metrics_launch((const float *)ctx->x[slot].p, nc, T, a, b,
+                                    d_thr ? d_thr + (size_t)c0 * n_doy * P : (const double *)ctx->aux[slot].p, n_doy, P, h_doy_map,
                                     h_defs, D, h_season_north, h_season_south, Y,
                                     h_is_south ? (const uint8_t *)ctx->south[slot].p : nullptr,
                                     (uint16_t *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));

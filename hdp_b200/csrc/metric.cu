@@ -166,7 +166,7 @@ k_unpack_mask(const uint32_t *__restrict__ hot, int64_t C, int64_t T, int P, int
 // ----------------------------------------------------------------------------------------------------
 // k_scan
 // ----------------------------------------------------------------------------------------------------
-static int g_scan_filter = 1;        // test hook (hdp_b200_metrics_run_filter): 0 = k_scan queues every run
+static std::atomic<int> g_scan_filter{1};        // test hook (hdp_b200_metrics_run_filter): 0 = k_scan queues every run
 
 struct ScanTables {
     uint32_t max_subs_plane[32];     // bit k of max_subs of every definition (bit-sliced constants)

@@ -1730,10 +1730,10 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     return L;
 }
 
-static int g_force_generic = 0;     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
-static int g_force_ranked = 0;
-static int g_seg_light = 1;          // test hook: 0 = the candidate path runs in k_thr_seg itself (no k_thr_cand)
-static int g_seg_candidates = 1;     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
+static std::atomic<int> g_force_generic{0};     // 1: k_thr_generic for everything; 2: k_thr_ranked instead of k_thr_seg
+static std::atomic<int> g_force_ranked{0};
+static std::atomic<int> g_seg_light{1};          // test hook: 0 = the candidate path runs in k_thr_seg itself (no k_thr_cand)
+static std::atomic<int> g_seg_candidates{1};     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
 
 // The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
 // capacity so that every chunk sees the tables at the same place) and `tables_resident` skips the table uploads when
@@ -1801,12 +1801,9 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_time, seg.seg_time.data(), sizeof(int) * seg.seg_time.size(), cudaMemcpyHostToDevice, st));
         if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.seg_ne, seg.seg_ne.data(), sizeof(int) * seg.seg_ne.size(), cudaMemcpyHostToDevice, st));
         if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.doy_rng, seg.doy_rng.data(), seg.doy_rng.size(), cudaMemcpyHostToDevice, st));
-        static bool attr_done = false;
         const size_t smem = (size_t)kSegWarps * kSegWarpBytes;
-        if (!attr_done) {
-            HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
+        // per launch, not latched per process: the attribute belongs to the current device's copy of the function
+        HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SegGeom geo = seg.geo;
         {
             // candidate filter (k_thr_seg phase 1b): every requested position is among the K largest of its window
@@ -1823,12 +1820,8 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         if (geo.cand_m > 0 && g_seg_light && (size_t)blocks <= L.handed_over_count) {
             // high quantiles: the light kernel first, then k_thr_seg for the warps it handed over (non-finite samples,
             // more than kLCap candidates), a small grid taking the blocks on the hand-over list in turns
-            static bool light_attr_done = false;
             const size_t smem_l = (size_t)kSegWarps * kLWarpBytes;
-            if (!light_attr_done) {
-                HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-                light_attr_done = true;
-            }
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
             HDP_CUDA_TRY(cudaMemsetAsync(L.handed_over, 0, sizeof(uint32_t) * (size_t)(1 + blocks), st));
             {
                 KernelTimer timer(kThrCand, st);

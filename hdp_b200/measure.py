@@ -16,9 +16,7 @@ HUMIDITY_UNITS = ["%", "g/g"]
 
 
 def _with_values(da, values, attrs=None, name=None):
-    out = xr.DataArray(values, dims=list(da.dims), coords={k: xr.coord_values(da, k) for k in da.coords},
-                       name=da.name if name is None else name, attrs=dict(da.attrs if attrs is None else attrs))
-    return out
+    return xr.with_values(da, values, attrs, name)
 
 
 def kelvin_to_celsius(temp):

@@ -105,7 +105,7 @@ def compute_individual_metrics(measure, threshold, hw_definitions: list, include
 
     st = _tables.hemisphere_ranges(time_axis)                       # compute_hemisphere_ranges, :410
     doy_map = _tables.doy_map(time_axis.dayofyr)                    # build_doy_map, :413
-    x, cell_dims, cell_shape = _layout.to_time_cells(xr.values_of(measure), tuple(measure.dims))
+    x, cell_dims, cell_shape = _layout.to_time_cells(xr.values_of(measure), tuple(measure.dims), require_float32=True)
     south = _tables.is_south(_layout.cell_latitudes(xr.coord_values(measure, "lat"), cell_dims, cell_shape))
 
     # thresholds [<cells in the measure's order>, doy, percentile] -> [C, n_doy, P]; exact coordinate join like apply_ufunc

@@ -58,6 +58,37 @@ def gather_cells(local, n_cells: int, dim: int = -1, group=None, align: int = CE
     if local.shape[dim] != c1 - c0:
         raise ValueError(f"rank {rank} holds {local.shape[dim]} cells, expected {c1 - c0}")
     widest = max(b - a for a, b in ranges)
+    even = all(b - a == widest for a, b in ranges)
+    dim = dim % local.dim()
+    if dim == 0 and even and local.is_contiguous():
+        # cell-major shards of equal size (thresholds [C, n_doy, P]): the gathered buffer IS the result, no repacking
+        as_bytes = local.view(torch.uint8) if local.dtype == torch.uint16 else local
+        bucket = torch.empty((world * as_bytes.shape[0],) + tuple(as_bytes.shape[1:]), dtype=as_bytes.dtype, device=as_bytes.device)
+        dist.all_gather_into_tensor(bucket, as_bytes, group=group)
+        return bucket.view(torch.uint16) if local.dtype == torch.uint16 else bucket
+    if dim == local.dim() - 1 and local.is_contiguous():
+        # cell-minor shards (metrics [4, P, D, Y, C]): every rank's block travels as it lies in memory ([rows, cells_r]); the
+        # blocks are then laid side by side along the cell axis with one strided copy each - no transposition, no padding pass
+        rows = 1
+        for n in local.shape[:-1]:
+            rows *= int(n)
+        flat = local.reshape(rows * (c1 - c0))
+        as_bytes = flat.view(torch.uint8) if flat.dtype == torch.uint16 else flat
+        per = rows * (2 if local.dtype == torch.uint16 else 1)       # bucket elements per cell (every rank agrees, empty shards too)
+        bucket = torch.empty((world, widest * per), dtype=as_bytes.dtype, device=as_bytes.device)
+        if even:
+            dist.all_gather_into_tensor(bucket.view(-1), as_bytes, group=group)
+        else:
+            mine = bucket[rank]
+            mine[: as_bytes.numel()].copy_(as_bytes)
+            dist.all_gather_into_tensor(bucket.view(-1), mine.clone(), group=group)
+        out = torch.empty(tuple(local.shape[:-1]) + (n_cells,), dtype=local.dtype, device=local.device)
+        out2 = out.view(rows, n_cells)
+        for r, (a, b) in enumerate(ranges):
+            blk = bucket[r, : (b - a) * per]
+            blk = blk.view(torch.uint16) if local.dtype == torch.uint16 else blk
+            out2[:, a:b].copy_(blk.view(rows, b - a))
+        return out
     moved = local.movedim(dim, 0).contiguous()
     if moved.shape[0] < widest:
         pad = torch.zeros((widest - moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
@@ -72,12 +103,26 @@ def gather_cells(local, n_cells: int, dim: int = -1, group=None, align: int = CE
     return torch.cat(parts, dim=0).movedim(0, dim)
 
 
+def member_pieces(c0: int, c1: int, grid_cells: int) -> List[Tuple[int, int, int]]:
+    """The flattened (member, grid cell) range ``[c0, c1)`` as ``(member, g0, g1)`` pieces, one per member it touches
+    (an ensemble sharded by flattened cell index: every piece meets the member-free thresholds of grid cells g0..g1)."""
+    pieces = []
+    c = c0
+    while c < c1:
+        m, g0 = divmod(c, grid_cells)
+        g1 = min(grid_cells, g0 + (c1 - c))
+        pieces.append((m, g0, g1))
+        c += g1 - g0
+    return pieces
+
+
 def run_sharded(base_tc, run_tc, window_tables, percentiles, doy_map, defs, season_north, season_south, is_south=None,
-                group=None, gather: bool = True, kernels=None):
+                group=None, gather: bool = True, kernels=None, local_of: Optional[int] = None, out=None):
     """Both paths on this rank's cells, then (optionally) the output gather.
 
     ``base_tc`` / ``run_tc`` are the FULL ``[T, C]`` float32 arrays as seen by this rank (views are taken, nothing is
-    copied) or already-local shards when ``gather`` is False.  Returns ``(thresholds [C, n_doy, P] float64,
+    copied).  With ``local_of = C`` they are instead this rank's shard of a ``C``-cell problem that no rank holds whole
+    (``is_south`` local as well); ``out = (thresholds, metrics)`` are optional preallocated local outputs.  Returns ``(thresholds [C, n_doy, P] float64,
     metrics [4, P, D, Y, C] uint16)``.  ``kernels`` defaults to the CUDA entry points of :mod:`hdp_b200._core`; the
     CPU tests inject a stand-in so that the partition/gather logic is exercised without a GPU."""
     import torch.distributed as dist
@@ -89,13 +134,23 @@ def run_sharded(base_tc, run_tc, window_tables, percentiles, doy_map, defs, seas
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if multi else 0
     world = dist.get_world_size(group) if multi else 1
-    C = base_tc.shape[1]
-    if run_tc.shape[1] != C:
+    if run_tc.shape[1] != base_tc.shape[1]:
         raise ValueError("baseline and measure must cover the same cells")
-    c0, c1 = cell_range(C, rank, world)
-    south = None if is_south is None else is_south[c0:c1]
-    thr = thresholds_fn(base_tc[:, c0:c1], window_tables, percentiles)
-    met = metrics_fn(run_tc[:, c0:c1], thr, doy_map, defs, season_north, season_south, south)
+    if local_of is None:
+        C = base_tc.shape[1]
+        c0, c1 = cell_range(C, rank, world)
+        south = None if is_south is None else is_south[c0:c1]
+        base_tc, run_tc = base_tc[:, c0:c1], run_tc[:, c0:c1]
+    else:
+        C = int(local_of)
+        c0, c1 = cell_range(C, rank, world)
+        if base_tc.shape[1] != c1 - c0:
+            raise ValueError(f"rank {rank} holds {base_tc.shape[1]} cells, expected {c1 - c0}")
+        south = is_south
+    kw_t = {} if out is None else {"out": out[0]}
+    kw_m = {} if out is None else {"out": out[1]}
+    thr = thresholds_fn(base_tc, window_tables, percentiles, **kw_t)
+    met = metrics_fn(run_tc, thr, doy_map, defs, season_north, season_south, south, **kw_m)
     if gather and multi:
         thr = gather_cells(thr, C, dim=0, group=group)
         met = gather_cells(met, C, dim=-1, group=group)

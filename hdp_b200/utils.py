@@ -71,6 +71,4 @@ def generate_test_rh_dataarray(start_date="2000-01-01", end_date="2049-12-31", g
     base = generate_test_control_dataarray(start_date=start_date, end_date=end_date, grid_shape=grid_shape)
     vals = xr.values_of(base)
     vals = np.abs(vals / vals.max() - 0.3)
-    out = xr.DataArray(vals, dims=list(base.dims), coords={k: xr.coord_values(base, k) for k in base.coords},
-                       name="test_rh_data", attrs={"units": "g/g"})
-    return out
+    return xr.with_values(base, vals, attrs={"units": "g/g"}, name="test_rh_data")

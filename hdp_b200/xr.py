@@ -197,9 +197,33 @@ def set_coord_attrs(ds, name: str, attrs: dict, replace: bool = False) -> None:
     target.update(attrs)
 
 
-def non_time_coords(da) -> "OrderedDict[str, object]":
+def coords_of(da, skip=()) -> "OrderedDict[str, object]":
+    """The coordinates of ``da`` in a form ``DataArray(coords=...)`` accepts back.
+
+    With real xarray the coordinate objects themselves are passed on: they carry their own dims, so non-dimension
+    coordinates that are not scalar (2-D ``lat``/``lon`` on curvilinear grids) survive, like the reference's
+    ``{**measure.coords}``.  Coordinates that live on a skipped dim (``time``, ``member``) are dropped with it.
+    The stand-in has dimension coordinates only and hands back their values."""
     out = OrderedDict()
     for name in da.coords:
-        if name != "time":
-            out[name] = coord_values(da, name)
+        c = da.coords[name]
+        if name in skip or any(d in skip for d in getattr(c, "dims", ())):
+            continue
+        out[name] = c if HAVE_XARRAY else coord_values(da, name)
     return out
+
+
+def non_time_coords(da) -> "OrderedDict[str, object]":
+    return coords_of(da, skip=("time",))
+
+
+def with_values(da, values, attrs=None, name=None):
+    """``da`` with new data of the same shape (same dims and coordinates), optionally new attrs / name."""
+    if HAVE_XARRAY:                        # pragma: no cover
+        out = da.copy(deep=False, data=values)
+        out.attrs = dict(da.attrs if attrs is None else attrs)
+        if name is not None:
+            out = out.rename(name)
+        return out
+    return DataArray(values, dims=list(da.dims), coords=coords_of(da), name=da.name if name is None else name,
+                     attrs=dict(da.attrs if attrs is None else attrs))

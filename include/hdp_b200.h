@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define HDP_B200_ABI_VERSION 1
+#define HDP_B200_ABI_VERSION 2
 
 #define HDP_B200_OK                 0
 #define HDP_B200_ERR_INVALID       (-1)  /* null pointer, negative size, quantile outside [0,1] or NaN, bad table entry */
@@ -85,10 +85,14 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
  * the candidate filter but without k_thr_cand. */
 void hdp_b200_thresholds_force_generic(int on);
 
+/* Host-buffer variant (chunked H2D / kernels / D2H pipeline, see csrc/host.cu).  d_keep: optional DEVICE buffer
+ * f64 [C, n_doy, P]; when given, the thresholds are also left there, so that the metric pass that follows
+ * (hdp_b200_metrics_host with d_thr = d_keep) does not upload them again - in the reference workflow
+ * compute_thresholds -> compute_group_metrics the thresholds then cross PCIe once (to the caller), not three times. */
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                              const double *h_q, int P,
-                             double *h_out);
+                             double *h_out, double *d_keep);
 
 /* ---------------------------------------------------------------------------------------------------
  * Path 2 - heatwave metrics.   reference: hdp/metric.py:11-172, 280-369
@@ -121,8 +125,10 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
  * that cannot change any result (short runs after long breaks, see metric.cu); the outputs must be identical. */
 void hdp_b200_metrics_run_filter(int on);
 
+/* Host-buffer variant.  Thresholds come from h_thr (host, uploaded chunk by chunk) unless d_thr (DEVICE f64
+ * [C, n_doy, P], e.g. the d_keep of hdp_b200_thresholds_host) is given, in which case h_thr may be NULL. */
 int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
-                          const double *h_thr, int n_doy, int P,
+                          const double *h_thr, const double *d_thr, int n_doy, int P,
                           const int32_t *h_doy_map,
                           const int32_t *h_defs, int D,
                           const int32_t *h_season_north, const int32_t *h_season_south, int Y,

@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference Numba kernels from /root/reference (build container only).
+"""Import the UNMODIFIED reference Numba kernels: from oracle/_ref/ (the pip-installed copy that
+oracle/build.py:build_ref() makes; it travels to the GPU box) or, failing that, from /root/reference
+(build container only).
 
-TEST INFRASTRUCTURE - not product code.  Only tests/golden/make_golden.py and the
-container-only cross-check tests use this module.  /root/reference does not exist on the
-GPU box, so nothing reachable from `-m gpu` tests, smoke() or bench.py may import it.
+TEST INFRASTRUCTURE - not product code.  Users: tests/golden/make_golden.py, the cross-check tests, and
+bench.py's CPU legs (cpu_baseline / --impl reference), which time these kernels as the reference baseline.
+Nothing on the GPU box reads /root/reference: there the only source is oracle/_ref/.
 
 The reference's hdp/threshold.py and hdp/metric.py import xarray, dask.array, cftime and
 tqdm at module level; none of those are installed in this image and they are only used by
@@ -14,7 +16,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HDP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.join(_HERE, "_ref")
+
+
+def _root() -> str:
+    if os.path.isfile(os.path.join(_INSTALLED, "hdp", "metric.py")):
+        return _INSTALLED
+    return os.environ.get("HDP_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _root()
 
 
 class _Stub(types.ModuleType):

@@ -430,7 +430,21 @@ def test_host_pipeline_many_chunks(core, monkeypatch, chunk):
     assert np.array_equal(core.metrics_host(xr, thr_h, *args), out_d)
     assert np.array_equal(core.metrics_host(np.ascontiguousarray(xr.T).T, thr_h, *args), out_d)
     assert np.array_equal(core.metrics_host(xr, thr_h, *args[:-1], None), core.metrics_array(dev(xr), thr_d, *args[:-1], None).cpu().numpy())
+    # thresholds that stay on the device between the two host calls (the compute_thresholds -> compute_group_metrics chain)
+    import torch
+    thr_k = core.thresholds_host(xb, wt, q, keep=True)
+    assert bits_equal(thr_k, thr_h) and not thr_k.flags.writeable
+    d_thr = core.resident_thresholds(thr_k)
+    assert d_thr is not None and torch.equal(d_thr, thr_d)
+    assert core.resident_thresholds(thr_k.reshape(C, -1, q.size)) is d_thr         # a same-memory view still hits
+    assert core.resident_thresholds(thr_k.copy()) is None and core.resident_thresholds(thr_h) is None
+    assert np.array_equal(core.metrics_host(xr, thr_k, *args), out_d)              # resident copy used (no upload)
+    assert np.array_equal(core.metrics_host(xr, thr_d, *args), out_d)              # explicit device tensor
+    keep = torch.empty_like(thr_d)
+    core.thresholds_host(xb, wt, q, out=np.empty_like(thr_h), keep=keep)
+    assert torch.equal(keep, thr_d)
     core.host_release()
+    assert core.resident_thresholds(thr_k) is None
     assert bits_equal(core.thresholds_host(xb, wt, q), thr_h)          # the context comes back after a release
 
 

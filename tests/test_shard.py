@@ -61,13 +61,19 @@ def _case(C):
                 is_south=(np.arange(C) % 3 == 0).astype(np.uint8))
 
 
-def _worker(rank, world, port, C, result_dir):
+def _worker(rank, world, port, C, result_dir, local=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         k = _case(C)
-        thr, met = shard.run_sharded(torch.from_numpy(k["base"]), torch.from_numpy(k["run"]), k["wt"], k["q"], k["dm"], k["defs"],
-                                     k["north"], k["south"], k["is_south"], kernels=_oracle_kernels())
+        if local:                       # every rank holds only its shard of a problem no rank holds whole (bench.py --gpus N)
+            c0, c1 = shard.cell_range(C, rank, world)
+            thr, met = shard.run_sharded(torch.from_numpy(k["base"][:, c0:c1].copy()), torch.from_numpy(k["run"][:, c0:c1].copy()),
+                                         k["wt"], k["q"], k["dm"], k["defs"], k["north"], k["south"], k["is_south"][c0:c1],
+                                         kernels=_oracle_kernels(), local_of=C)
+        else:
+            thr, met = shard.run_sharded(torch.from_numpy(k["base"]), torch.from_numpy(k["run"]), k["wt"], k["q"], k["dm"], k["defs"],
+                                         k["north"], k["south"], k["is_south"], kernels=_oracle_kernels())
         np.savez(os.path.join(result_dir, f"rank{rank}.npz"), thr=thr.numpy(), met=met.numpy().astype(np.int64))
         # a gathered tensor must also round-trip for 1-D per-cell vectors
         c0, c1 = shard.cell_range(C, rank, world)
@@ -77,10 +83,22 @@ def _worker(rank, world, port, C, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,C", [(2, 70), (3, 101), (2, 20)])
-def test_sharded_run_equals_single_process(tmp_path, world, C):
+def test_member_pieces():
+    assert shard.member_pieces(0, 10, 10) == [(0, 0, 10)]
+    assert shard.member_pieces(5, 27, 10) == [(0, 5, 10), (1, 0, 10), (2, 0, 7)]
+    assert shard.member_pieces(7, 7, 10) == []
+    grid, members, world = 55296, 50, 8
+    seen = []
+    for r in range(world):
+        c0, c1 = shard.cell_range(grid * members, r, world)
+        seen += [(m * grid + g0, m * grid + g1) for m, g0, g1 in shard.member_pieces(c0, c1, grid)]
+    assert seen[0][0] == 0 and seen[-1][1] == grid * members and all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+
+
+@pytest.mark.parametrize("world,C,local", [(2, 70, False), (3, 101, False), (2, 20, False), (2, 128, False), (2, 128, True), (3, 101, True)])
+def test_sharded_run_equals_single_process(tmp_path, world, C, local):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, C, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, C, str(tmp_path), local), nprocs=world, join=True)
     k = _case(C)
     thresholds, metrics = _oracle_kernels()
     thr = thresholds(torch.from_numpy(k["base"]), k["wt"], k["q"])

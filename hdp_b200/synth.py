@@ -69,12 +69,14 @@ def grid_latitudes(n_lat: int, n_lon: int) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.0, offset: float = 0.0,
-                  sigma: float = 3.0, ar: float = 0.7, device="cuda", chunk_days: int = 2048):
+                  sigma: float = 3.0, ar: float = 0.7, device="cuda", chunk_days: int = 2048, cols=None):
     """float32 ``[T, C]`` on ``device``:
     ``15 + offset + 12 cos(lat) sin(2 pi (doy-110)/365) sgn(lat) - 25 |lat|/90 + trend t/T + sigma AR(1)``.
 
     The AR(1) term is the stationary filter ``sqrt(1-ar^2) * sum_k ar^k e[t-k]`` truncated at 32 lags
     (ar^32 ~ 1e-5), so every time chunk can be generated independently and reproducibly from the seed.
+    ``cols = (g0, g1)`` keeps only cells g0..g1 of the field (a shard): the values are those of the full field, whoever
+    generates them, because the noise is always drawn for the whole grid.
     """
     import torch
     dev = torch.device(device)
@@ -84,7 +86,8 @@ def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.
     doy = torch.as_tensor(np.asarray(dayofyr, dtype=np.float32), device=dev)
     amp = 12.0 * torch.cos(torch.deg2rad(lat)) * torch.where(lat < 0, -1.0, 1.0)
     base = 15.0 + offset - 25.0 * lat.abs() / 90.0
-    out = torch.empty((T, C), dtype=torch.float32, device=dev)
+    g0, g1 = (0, C) if cols is None else (int(cols[0]), int(cols[1]))
+    out = torch.empty((T, g1 - g0), dtype=torch.float32, device=dev)
     lags = 32
     w = (ar ** torch.arange(lags, device=dev, dtype=torch.float32)) * float(np.sqrt(1 - ar * ar)) * sigma
     for t0 in range(0, T, chunk_days):
@@ -102,6 +105,8 @@ def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.
             e[: t0 - lo] = eprev[lo - prev0:]
             del eprev
         e[t0 - lo:] = torch.randn((t1 - t0, C), generator=gen, dtype=torch.float32, device=dev)
+        if cols is not None:
+            e = e[:, g0:g1].contiguous()
         seg = out[t0:t1]
         seg.zero_()
         for k in range(lags):
@@ -113,6 +118,6 @@ def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.
                 seg += w[k] * e[a: a + (t1 - t0)]
         tt = torch.arange(t0, t1, device=dev, dtype=torch.float32)
         season = torch.sin(2 * np.pi * (doy[t0:t1] - 110.0) / 365.0)
-        seg += base[None, :] + season[:, None] * amp[None, :] + (trend * tt / T)[:, None]
+        seg += base[None, g0:g1] + season[:, None] * amp[None, g0:g1] + (trend * tt / T)[:, None]
         del e
     return out

@@ -34,6 +34,7 @@ class Workload:
     base_start: int = 1961
     run_start: int = 2015
     description: str = ""
+    members: int = 1                   # ensemble members of the metric run that share ONE member-free threshold table
     _cache: dict = field(default_factory=dict, repr=False)
 
     @property
@@ -78,7 +79,7 @@ class Workload:
 
     def cell_years(self, cells: int = None) -> int:
         C = self.cells if cells is None else cells
-        return C * (self.base_years + self.run_years) * self.measures
+        return C * (self.base_years + self.members * self.run_years) * self.measures
 
 
 def get(name: str) -> Workload:
@@ -95,4 +96,8 @@ def get(name: str) -> Workload:
     if name == "lens_member":
         return Workload(name, 192, 288, 30, 86, 1, np.arange(0.9, 1.0, 0.01), README_DEFS,
                         description="one CESM2-LENS-like member: 192x288, 30-year baseline + 86-year run")
+    if name == "lens50":
+        return Workload(name, 192, 288, 30, 86, 1, np.arange(0.9, 1.0, 0.01), README_DEFS, members=50,
+                        description="CESM2-LENS-like 192x288, 50 ensemble members x 86 years against one 30-year baseline, "
+                                    "sharded by flattened (member, cell) index across the GPUs")
     raise KeyError(name)

@@ -3,7 +3,7 @@ comparison with the CPU oracle on cells sampled across the whole grid (the oracl
 
     cmip6_1deg    180 x 360, 30-year baseline + 86-year run, 10 percentiles x 6 definitions        (configs[1], the bench)
     lens_member   192 x 288, one CESM2-LENS-like member                                            (configs[2], per GPU)
-    era5_025deg   0.25 deg, 30-year baseline, 31-day window, standard calendar: a 90-row latitude band of the 721 x 1440 grid
+    era5_025deg   0.25 deg, 30-year baseline, 31-day window, standard calendar: the whole 721 x 1440 grid     (configs[3])
     wide_sweep    1 deg, 20 percentiles x 24 definitions                                           (configs[4])
 """
 import numpy as np
@@ -132,12 +132,40 @@ def test_lens_member_full_grid(core):
     _run(core, wl, lat, 99, 48)
 
 
-def test_era5_band_thresholds(core):
+def test_era5_full_grid_thresholds(core):
+    # the whole 721 x 1440 grid (1 038 240 cells): 45.5 GB of samples in, 30.4 GB of thresholds out, standard calendar
+    # (366 day-of-year rows, -1 pads), 31-day window.  Properties are checked band by band to bound the temporaries.
     from hdp_b200 import synth, workloads
     wl = workloads.get("era5_025deg")
     lat, _ = synth.grid_latitudes(wl.n_lat, wl.n_lon)
-    band = lat[300 * wl.n_lon: 390 * wl.n_lon]                         # 90 of the 721 latitude rows: 129 600 cells, 5.7 GB
-    _run(core, wl, band, 7, 24)
+    base, _ = _fields(wl, lat, 7, run=False)
+    thr = core.thresholds_array(base, wl.window_tables(), wl.percentiles)
+    q = np.asarray(wl.percentiles)
+    step = 64 * wl.n_lon
+    for c0 in range(0, lat.size, step):
+        _check_threshold_properties(base[:, c0:c0 + step], thr[c0:c0 + step], q)
+    _oracle_sample(core, wl, lat, base, None, thr, None, 24, 7)
+
+
+def test_run_sharded_on_gpu_world1(core):
+    # the product's shard entry point with the CUDA kernels (world size 1: the partition is the whole range, no collective),
+    # full-array and local-shard forms, against the oracle; the N > 1 partition + gather logic is covered over gloo in test_shard.py
+    from hdp_b200 import _tables as tb, shard, synth, workloads
+    wl = workloads.get("lens_member")
+    lat, _ = synth.grid_latitudes(wl.n_lat, wl.n_lon)
+    lat = lat[::37][:1000]
+    base, warm = _fields(wl, lat, 11)
+    st, dm = wl.seasons(), tb.doy_map(wl.run_axis().dayofyr)
+    south = torch.as_tensor((lat < 0).astype(np.uint8), device="cuda")
+    thr, out = shard.run_sharded(base, warm, wl.window_tables(), wl.percentiles, dm, wl.defs, st.north, st.south, south)
+    _oracle_sample(core, wl, lat, base, warm, thr, out, 16, 3)
+    thr2 = torch.empty_like(thr); out2 = torch.empty_like(out)
+    shard.run_sharded(base, warm, wl.window_tables(), wl.percentiles, dm, wl.defs, st.north, st.south, south,
+                      gather=False, local_of=lat.size, out=(thr2, out2))
+    assert torch.equal(thr2.view(torch.int64), thr.view(torch.int64)) and torch.equal(out2.view(torch.int16), out.view(torch.int16))
+    for m, g0, g1 in shard.member_pieces(100, 900, 400):               # pieces of a member-sharded range meet their thresholds
+        piece = core.metrics_array(warm[:, g0:g1], thr[g0:g1], dm, wl.defs, st.north, st.south, south[g0:g1])
+        assert torch.equal(piece.view(torch.int16), out.view(torch.int16)[..., g0:g1])
 
 
 def test_wide_sweep_full_grid(core):

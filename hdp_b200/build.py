@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libhdp_b200.so")
 SOURCES = ["abi.cu", "threshold.cu", "thr_net.cu", "metric.cu", "measure.cu", "host.cu"]
-HEADERS = ["common.cuh", "thr_net_gen.cuh"]
+HEADERS = ["common.cuh", "thr_net.cuh", "thr_net_gen.cuh"]
 OBJ = os.path.join(HERE, "_obj")
 
 NVCC_FLAGS = [

@@ -1,0 +1,317 @@
+// thr_net.cu - k_thr_net: path 1 (thresholds) for high quantiles, one grid cell per LANE, everything in registers.
+//
+// Replaces (reference = AgentOxygen/HDP v1.0.2) the same code as threshold.cu: compute_percentiles (hdp/threshold.py:52-78)
+// looped over cells (:81-93) with Numba's np.quantile arithmetic (numba/np/arraymath.py:1655-1704).
+//
+// Idea.  Every requested position lies among the K largest samples of its window (K = 46 of 450 for q >= 0.9, 15-day window,
+// 30 years), and a window is W consecutive day-of-year rows of n_y samples each.  So:
+//   * a row is ordered ONCE per use by a sorting network (compare-exchange = one FMNMX pair, no branches, no shared memory),
+//   * "the K largest of rows i..j" are kept as descending K-lists and combined with merge networks (K largest of two lists),
+//   * the sliding window is decomposed so that no list ever has to forget a row: rows are cut into blocks of s = W / 3 rows and
+//         window(b, i) = suffix_i(block b)  u  block b+1  u  block b+2  u  prefix_i(block b+3)        (van Herk / Gil-Werman)
+//     where suffix lists grow backwards through block b, prefix lists grow forwards through block b+3, and the pair of full
+//     blocks in the middle is one merge per block.  (Windows with W not divisible by 3 use one block per window: suffix u prefix.)
+// A lane owns one cell, a warp 32 neighbouring cells: every load of a day is one full 128-byte line, there is no gather tile, no
+// atomics, no bank conflict, no divergence - the instruction stream is identical for all cells.  Lists that must outlive a row
+// step wait in shared memory ([element][lane], conflict-free); s + 1 lists of K floats per cell.
+// The networks come from tools/gen_networks.py (thr_net_gen.cuh): pruned odd-even merges and Knuth's merge exchange.
+//
+// Results are the reference's, bit for bit: selecting order statistics exactly is order-independent, and the interpolation is the
+// same separately rounded f64 expression as in threshold.cu.  Cells with NaN / +-inf samples (the reference has special rules for
+// them) are detected on the fly and handed to k_thr_seg through its hand-over list; days whose window is not W consecutive rows
+// (the reference's mirrored year end, threshold.py:45-47) are pooled row by row from the window table.
+#include <math.h>
+#include <algorithm>
+#include <map>
+
+#include "thr_net.cuh"
+#include "thr_net_gen.cuh"
+
+// Template instances that exist (samples per row NY x list length K x blocks per window M).  net_plan picks the smallest
+// NY >= n_y (30 exactly for 30-year baselines) and the smallest K >= the deepest requested position; every combination of the
+// two menus must be listed.
+#ifndef HDP_NET_FULL
+#define HDP_NET_NY_MENU 32
+#define HDP_NET_K_MENU 48
+#define HDP_NET_INSTANCES(X) X(30, 48, 3) X(30, 48, 1) X(32, 48, 3) X(32, 48, 1)
+#endif
+
+namespace hdp {
+
+// Pads (rows shorter than NY, lists shorter than K, rows past the end of the sequence) are the most negative FINITE float: they
+// sort below every sample, never reach a requested position (a window holds at least K real samples), and - unlike -inf - do not
+// trip the non-finite census.
+#define HDP_NET_PAD (-3.402823466e+38f)
+
+struct NetStepDesc {            // what one row step does besides "order the row and merge it into the running list" (warp-uniform)
+    int reset;                  // the running list starts over with this row
+    int other;                  // slot of the stored list to combine the running list with (-1: none)
+    int store_dst;              // slot that receives the combination (-1: none)
+    int store_run;              // slot that receives the running list itself (-1: none)
+    int emit_day;               // day of year whose thresholds the combination yields (-1: none)
+    int emit_slot;              // scratch slot for the rank lookup
+};
+
+template <int NY>
+__device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *xc, int64_t ld_t, const int *__restrict__ tt)
+{
+#pragma unroll
+    for (int y = 0; y < NY; y++) {
+        const int t = __ldg(tt + y);                              // warp-uniform
+        raw[y] = t >= 0 ? __ldg(xc + (int64_t)t * ld_t) : HDP_NET_PAD;
+    }
+}
+
+template <int NY, int K, int M>
+__global__ void __launch_bounds__(32)
+k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
+          const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
+          const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x;
+    const float ninf = HDP_NET_PAD;
+    const int64_t n_regular = g.n_tiles * g.n_chunks;
+    const int64_t item = blockIdx.x;
+    const bool irregular = item >= n_regular;
+    const int64_t tile = irregular ? item - n_regular : item / g.n_chunks;
+    const int chunk = irregular ? 0 : (int)(item - tile * g.n_chunks);
+    const int64_t c = tile * 32 + lane;
+    const bool valid = c < C;
+    const float *xc = x + (valid ? c : C - 1);
+    float *my = sm + lane;                                        // element e of slot j: my[(j * K + e) * 32]
+    const int s = g.s;
+    constexpr int kPro = M == 3 ? 2 : 0;                          // prologue blocks of a chunk (the two full blocks after its first one)
+    const int slot_f = s;                                         // M == 3: slot 0 = the pair of full blocks, slots 1..s-1 = suffix lists, slot s = last full block
+
+    const int b0 = chunk * g.steps_per_chunk, b1 = min(b0 + g.steps_per_chunk, g.n_steps);
+    const int n_rows = irregular ? g.n_irr * g.W : (kPro + 2 * (b1 - b0)) * s;
+
+    // (pb, it): block phase and row inside it; the row table of step (pb, it)
+    auto row_table = [&](int n, int pb, int it) -> const int * {
+        if (irregular) return irr_time + (size_t)n * NY;
+        int row;
+        if (pb < kPro) row = (b0 + 1 + pb) * s + it;
+        else {
+            const int q = pb - kPro, b = b0 + (q >> 1);
+            row = (q & 1) ? (b + M) * s + it : b * s + (s - 1 - it);
+        }
+        return seq_time + (size_t)min(row, g.n_seq) * NY;        // rows past the sequence: the all-pad row
+    };
+
+    float raw[NY];
+    float run[K];
+    float bad_acc = 0.0f;
+    if (n_rows > 0) net_issue_loads<NY>(raw, xc, ld_t, row_table(0, 0, 0));
+#pragma unroll
+    for (int e = 0; e < K; e++) run[e] = ninf;
+
+    int pb = 0, it = 0;                                           // irregular items: pb = day, it = row of its window
+    const int per = irregular ? g.W : s;
+    for (int n = 0; n < n_rows; n++) {
+        float v[NY];
+#pragma unroll
+        for (int y = 0; y < NY; y++) {
+            v[y] = raw[y];
+            bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);             // non-finite census on the otherwise idle FMA pipe: NaN or +-inf -> NaN
+        }
+        int pb_n = pb, it_n = it + 1;
+        if (it_n == per) { it_n = 0; pb_n++; }
+        if (n + 1 < n_rows) net_issue_loads<NY>(raw, xc, ld_t, row_table(n + 1, pb_n, it_n));   // in flight while this row is worked on
+
+        // ---- what this step does
+        NetStepDesc d{it == 0, -1, -1, -1, -1, 0};
+        if (irregular) {
+            if (it == per - 1) d.emit_day = irr_day[pb];
+        } else if (pb < kPro) {
+            if (it == s - 1) {
+                d.store_run = slot_f;
+                if (pb == 1) { d.other = slot_f; d.store_dst = 0; }
+            }
+        } else {
+            const int q = pb - kPro, b = b0 + (q >> 1);
+            if (!(q & 1)) {                                       // suffix lists of block b, last row first
+                const int i = s - 1 - it;
+                if (M == 3) d.other = 0;
+                if (i > 0) { if (M == 3) d.store_dst = i; else d.store_run = i; }
+                else { d.emit_day = win_day[b * s]; d.emit_slot = 0; if (d.emit_day < 0) d.other = -1; }
+            } else if (it < s - 1) {                              // prefix lists of block b + M: window (b, it + 1)
+                d.emit_day = win_day[b * s + it + 1];
+                if (d.emit_day >= 0) { d.other = it + 1; d.emit_slot = it + 1; }
+            } else if (M == 3) {                                  // block b + 3 is complete: next pair of full blocks
+                d.other = slot_f; d.store_dst = 0; d.store_run = slot_f;
+            }
+        }
+
+        // ---- order the row, merge it into the running list
+        net::Sort<NY>::run(v);
+        if (d.reset) {
+#pragma unroll
+            for (int e = 0; e < K; e++) run[e] = e < NY ? v[e < NY ? e : 0] : ninf;
+        } else {
+            net::Merge<K, NY>::run(run, v);
+        }
+
+        // ---- combine with a stored list, store / look up the requested ranks
+        if (d.other >= 0 || d.emit_day >= 0) {
+            float tmp[K];
+            if (d.other >= 0) {
+                const float *o = my + (size_t)d.other * K * 32;
+#pragma unroll
+                for (int e = 0; e < K; e++) tmp[e] = o[e * 32];
+                net::Merge<K, K>::run(tmp, run);
+            } else {
+#pragma unroll
+                for (int e = 0; e < K; e++) tmp[e] = run[e];
+            }
+            if (d.store_dst >= 0) {
+                float *o = my + (size_t)d.store_dst * K * 32;
+#pragma unroll
+                for (int e = 0; e < K; e++) o[e * 32] = tmp[e];
+            }
+            if (d.emit_day >= 0) {
+                float *o = my + (size_t)d.emit_slot * K * 32;
+#pragma unroll
+                for (int e = 0; e < K; e++) o[e * 32] = tmp[e];
+                if (valid) {
+                    double *dst = out + ((size_t)c * g.n_doy + d.emit_day) * g.P;
+                    for (int p = 0; p < g.P; p++) {
+                        const double lower = (double)o[sel.idx_lo[p] * 32], upper = (double)o[sel.idx_hi[p] * 32];
+                        // numba/np/arraymath.py:1697-1701 (separately rounded), :1669-1675 for q == 1
+                        dst[p] = sel.is_max[p] ? upper : __dadd_rn(__dmul_rn(lower, sel.w_lo[p]), __dmul_rn(upper, sel.w_hi[p]));
+                    }
+                }
+            }
+        }
+        if (d.store_run >= 0) {
+            float *o = my + (size_t)d.store_run * K * 32;
+#pragma unroll
+            for (int e = 0; e < K; e++) o[e * 32] = run[e];
+        }
+        pb = pb_n; it = it_n;
+    }
+
+    // ---- cells with NaN / +-inf samples: all their segments go onto k_thr_seg's hand-over list (it runs behind this kernel)
+    if (valid && bad_acc != bad_acc && hand.list) {
+        const int group = (int)(c / hand.group_cells), w = (int)(c - (int64_t)group * hand.group_cells);
+        const int chunk_g = group / hand.gc, gcc = min(hand.gc, hand.n_groups - chunk_g * hand.gc);
+        for (int sg = 0; sg < hand.n_seg; sg++) {
+            const unsigned bid = (unsigned)(chunk_g * (hand.n_seg * hand.gc) + sg * gcc + (group - chunk_g * hand.gc));
+            if (atomicOr(&hand.list[1 + bid], 1u << w) == 0u) hand.list[1 + hand.n_blocks + atomicAdd(&hand.list[0], 1u)] = bid;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------------------
+static int pick(const int *menu, int n_menu, int need)
+{
+    for (int i = 0; i < n_menu; i++) if (menu[i] >= need) return menu[i];
+    return 0;
+}
+
+void net_set_cells(NetPlan &pl, int64_t C)
+{
+    NetGeom &g = pl.geo;
+    g.n_tiles = (C + 31) / 32;
+    // chunks of super-steps: enough items for ~8 waves of resident warps, but a chunk's two prologue blocks stay a small part of it
+    const int64_t want = 148 * 6 * 8;
+    int chunks = (int)std::min<int64_t>((want + g.n_tiles - 1) / std::max<int64_t>(g.n_tiles, 1), std::max(1, g.n_steps / 4));
+    chunks = std::max(1, std::min(chunks, g.n_steps));
+    g.steps_per_chunk = (g.n_steps + chunks - 1) / chunks;
+    g.n_chunks = (g.n_steps + g.steps_per_chunk - 1) / g.steps_per_chunk;
+}
+
+void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, int n_doy, int n_y, int W,
+              const int *pos_lo, const int *pos_hi, const int *mode_is_max, const int *mode_is_interp, const double *w_lo, const double *w_hi,
+              int P, int64_t C, NetPlan &pl)
+{
+    pl.usable = false;
+    NetGeom &g = pl.geo;
+    if (!(W & 1) || n_doy < 2 * W || n_y < 1) return;
+    const int r = W / 2;
+    static const int ny_menu[] = {HDP_NET_NY_MENU}, k_menu[] = {HDP_NET_K_MENU};
+    g.NY = n_y == 30 ? 30 : pick(ny_menu, (int)(sizeof(ny_menu) / sizeof(int)), n_y);
+    if (!g.NY) return;
+    g.M = W % 3 == 0 ? 3 : 1;
+    g.s = W / g.M;
+    if (g.M == 1 && W > 13) return;
+    // requested positions, from the top of the window
+    const int64_t n = (int64_t)W * n_y;
+    int k_top = 1;
+    for (int p = 0; p < P; p++) {
+        if (!mode_is_max[p] && !mode_is_interp[p]) return;                      // q == 0: the minimum is not among the largest
+        const int64_t lo = n - 1 - pos_lo[p], hi = n - 1 - pos_hi[p];
+        if (lo < 0 || hi < 0 || lo > 1000 || hi > lo) return;
+        k_top = std::max<int>(k_top, (int)lo + 1);
+        pl.sel.idx_lo[p] = (int)lo; pl.sel.idx_hi[p] = (int)hi; pl.sel.is_max[p] = mode_is_max[p];
+        pl.sel.w_lo[p] = w_lo[p]; pl.sel.w_hi[p] = w_hi[p];
+        if (mode_is_max[p]) pl.sel.idx_lo[p] = pl.sel.idx_hi[p] = 0;
+    }
+    g.K = pick(k_menu, (int)(sizeof(k_menu) / sizeof(int)), k_top);
+    if (!g.K || k_top > n) return;
+    g.W = W; g.n_y = n_y; g.n_doy = n_doy; g.P = P;
+    g.n_seq = n_doy + r;
+    g.n_win = n_doy - r;                                                         // windows 0 .. n_doy-r-1 = sequence rows [k, k + W)
+    g.n_steps = (g.n_win + g.s - 1) / g.s;
+    g.smem = (size_t)(g.M == 3 ? g.s + 1 : std::max(g.s, 1)) * g.K * 32 * sizeof(float);
+    if (g.smem > 227 * 1024) return;
+
+    auto time_of = [&](int row, int y) -> int {
+        if (y >= n_y) return -1;
+        int64_t t = time_index[(size_t)row * n_y + y];
+        if (t < 0) t += T_b;                                                     // -1 pads read the LAST sample (threshold.py:35,77)
+        return (int)t;
+    };
+    // the linear row sequence -r .. n_doy-1 (rows before 0 wrap to the end of the year, threshold.py:44-48)
+    pl.seq_time.assign((size_t)(g.n_seq + 1) * g.NY, -1);
+    for (int k = 0; k < g.n_seq; k++) {
+        const int row = ((k - r) % n_doy + n_doy) % n_doy;
+        for (int y = 0; y < g.NY; y++) pl.seq_time[(size_t)k * g.NY + y] = time_of(row, y);
+    }
+    // day d is regular if its window is exactly the sequence rows [d, d + W)
+    pl.win_day.assign((size_t)g.n_steps * g.s, -1);
+    pl.irr_day.clear(); pl.irr_time.clear();
+    std::vector<int> want(W), have(W);
+    for (int d = 0; d < n_doy; d++) {
+        bool regular = d < g.n_win;
+        if (regular) {
+            for (int j = 0; j < W; j++) { want[j] = ((d - r + j) % n_doy + n_doy) % n_doy; have[j] = win_rows[(size_t)d * W + j]; }
+            std::sort(want.begin(), want.end()); std::sort(have.begin(), have.end());
+            regular = want == have;
+        }
+        if (regular) { pl.win_day[d] = d; continue; }
+        pl.irr_day.push_back(d);
+        for (int j = 0; j < W; j++)
+            for (int y = 0; y < g.NY; y++) pl.irr_time.push_back(time_of(win_rows[(size_t)d * W + j], y));
+    }
+    g.n_irr = (int)pl.irr_day.size();
+    if (g.n_irr * 4 > n_doy) return;                                             // mostly irregular tables: not this kernel
+    net_set_cells(pl, C);
+    pl.usable = true;
+}
+
+template <int NY, int K, int M>
+static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out,
+                        const NetHandOver &hand, cudaStream_t st)
+{
+    const NetGeom &g = pl.geo;
+    HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net<NY, K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
+    if (items > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
+    k_thr_net<NY, K, M><<<(unsigned)items, 32, g.smem, st>>>(x, C, ld_t, tb.seq_time, tb.win_day, tb.irr_day, tb.irr_time, g, pl.sel, out, hand);
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
+}
+
+int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st)
+{
+    const NetGeom &g = pl.geo;
+#define HDP_NET_CASE(ny, k, m) if (g.NY == ny && g.K == k && g.M == m) return net_launch_t<ny, k, m>(pl, tb, x, C, ld_t, out, hand, st);
+    HDP_NET_INSTANCES(HDP_NET_CASE)
+#undef HDP_NET_CASE
+    return HDP_B200_ERR_UNSUPPORTED;
+}
+
+}  // namespace hdp

@@ -22,9 +22,11 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <memory>
 #include <mutex>
 
 #include "common.cuh"
+#include "thr_net.cuh"
 
 namespace hdp {
 
@@ -1707,6 +1709,7 @@ struct ThrLayout {
     uint8_t *doy_rng = nullptr;
     uint32_t *handed_over = nullptr;                 // per k_thr_cand block: the warps left to k_thr_seg
     size_t handed_over_count = 0;
+    NetTables net;                                   // k_thr_net tables
 };
 
 static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_norm, int n_doy, int n_y, int W)
@@ -1726,6 +1729,10 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     const int s_min = std::max(1, W / 2);
     L.handed_over_count = (size_t)(C / kSegWarps + 2 + thr_chunk_groups(T_b)) * (size_t)((n_doy + s_min - 1) / s_min);
     L.handed_over = cv.take<uint32_t>(1 + 2 * L.handed_over_count);       // count, flags[blocks], list[blocks]
+    L.net.seq_time = cv.take<int>((size_t)(n_doy + W / 2 + 1) * 32);      // k_thr_net: <= 32 samples per row, n_doy + r rows + the pad row
+    L.net.win_day = cv.take<int>((size_t)n_doy + W);
+    L.net.irr_day = cv.take<int>((size_t)n_doy);
+    L.net.irr_time = cv.take<int>((size_t)(n_doy / 4 + 1) * W * 32);      // at most a quarter of the days are irregular (net_plan)
     L.total = cv.off;
     return L;
 }
@@ -1734,6 +1741,19 @@ static std::atomic<int> g_force_generic{0};     // 1: k_thr_generic for everythi
 static std::atomic<int> g_force_ranked{0};
 static std::atomic<int> g_seg_light{1};          // test hook: 0 = the candidate path runs in k_thr_seg itself (no k_thr_cand)
 static std::atomic<int> g_seg_candidates{1};     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
+static std::atomic<int> g_net{1};                // test hook: 0 = no k_thr_net (the lane-per-cell network kernel, thr_net.cu)
+
+// Everything that depends on the tables and quantiles only, built once per distinct (tables, quantiles) and shared by the
+// calls that use them (the lock covers the lookup, not the launches: calls on different devices / streams do not serialise).
+struct ThrPlans {
+    std::vector<int32_t> rows, ti;
+    std::vector<double> q;
+    int64_t dims[4] = {0, 0, 0, 0};
+    RankedPlan ranked;
+    SegPlan seg;
+    NetPlan net;
+    SelTable sel;
+};
 
 // The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
 // capacity so that every chunk sees the tables at the same place) and `tables_resident` skips the table uploads when
@@ -1773,27 +1793,35 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
     }
     if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
 
-    // plans depend on the tables only: keep the last one (calls are serialised on the host side; the launches are asynchronous)
-    static std::mutex plan_mu;
-    std::lock_guard<std::mutex> plan_lock(plan_mu);
-    static std::vector<int32_t> cached_rows, cached_ti;
-    static std::vector<double> cached_q;
-    static int64_t cached_dims[4] = {0, 0, 0, 0};
-    static RankedPlan plan;
-    static SegPlan seg;
-    const size_t n_ti = (size_t)n_doy * n_y, n_wr = (size_t)n_doy * W;
-    const bool same = cached_dims[0] == n_doy && cached_dims[1] == n_y && cached_dims[2] == W && cached_dims[3] == T_b &&
-                      cached_rows.size() == n_wr && std::equal(cached_rows.begin(), cached_rows.end(), h_win_rows) &&
-                      cached_ti.size() == n_ti && std::equal(cached_ti.begin(), cached_ti.end(), h_time_index) &&
-                      cached_q.size() == (size_t)P && std::equal(cached_q.begin(), cached_q.end(), h_q);
-    if (!same) {
-        plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, plan);
-        plan_seg(h_time_index, h_win_rows, T_b, n_doy, n_y, W, seg);
-        cached_rows.assign(h_win_rows, h_win_rows + n_wr);
-        cached_ti.assign(h_time_index, h_time_index + n_ti);
-        cached_q.assign(h_q, h_q + P);
-        cached_dims[0] = n_doy; cached_dims[1] = n_y; cached_dims[2] = W; cached_dims[3] = T_b;
+    std::shared_ptr<ThrPlans> plans;
+    {
+        static std::mutex plan_mu;
+        static std::shared_ptr<ThrPlans> cached;
+        std::lock_guard<std::mutex> plan_lock(plan_mu);
+        const size_t n_ti = (size_t)n_doy * n_y, n_wr = (size_t)n_doy * W;
+        const bool same = cached && cached->dims[0] == n_doy && cached->dims[1] == n_y && cached->dims[2] == W && cached->dims[3] == T_b &&
+                          cached->rows.size() == n_wr && std::equal(cached->rows.begin(), cached->rows.end(), h_win_rows) &&
+                          cached->ti.size() == n_ti && std::equal(cached->ti.begin(), cached->ti.end(), h_time_index) &&
+                          cached->q.size() == (size_t)P && std::equal(cached->q.begin(), cached->q.end(), h_q);
+        if (!same) {
+            auto fresh = std::make_shared<ThrPlans>();
+            plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, fresh->ranked);
+            plan_seg(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->seg);
+            fill_sel(fresh->sel, b, h_q, P);
+            int is_max[HDP_B200_MAX_PERCENTILES], is_interp[HDP_B200_MAX_PERCENTILES];
+            for (int p = 0; p < P; p++) { is_max[p] = fresh->sel.mode[p] == kSelMax; is_interp[p] = fresh->sel.mode[p] == kSelInterp; }
+            net_plan(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->sel.pos_lo, fresh->sel.pos_hi, is_max, is_interp,
+                     fresh->sel.w_lo, fresh->sel.w_hi, P, C, fresh->net);
+            fresh->rows.assign(h_win_rows, h_win_rows + n_wr);
+            fresh->ti.assign(h_time_index, h_time_index + n_ti);
+            fresh->q.assign(h_q, h_q + P);
+            fresh->dims[0] = n_doy; fresh->dims[1] = n_y; fresh->dims[2] = W; fresh->dims[3] = T_b;
+            cached = fresh;
+        }
+        plans = cached;
     }
+    const RankedPlan &plan = plans->ranked;
+    const SegPlan &seg = plans->seg;
     const int E = n_doy * n_y;
     if (seg.usable && !g_force_generic && !g_force_ranked) {
         SelTable sel;
@@ -1817,6 +1845,33 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         const int64_t n_chunks = (geo.n_groups + geo.gc - 1) / geo.gc;
         const int64_t blocks = n_chunks * geo.n_seg * geo.gc;
         if (blocks > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
+        if (plans->net.usable && g_net && g_seg_light && g_seg_candidates && (size_t)blocks <= L.handed_over_count) {
+            // high quantiles, regular windows: the lane-per-cell network kernel; cells with NaN / +-inf samples put all their
+            // segments on k_thr_seg's hand-over list, which runs behind it (8 us when the list is empty)
+            NetPlan net = plans->net;                                           // (tables are shared; the cell split is per call)
+            net_set_cells(net, C);
+            if (!tables_resident) {
+                HDP_CUDA_TRY(cudaMemcpyAsync(L.net.seq_time, net.seq_time.data(), sizeof(int) * net.seq_time.size(), cudaMemcpyHostToDevice, st));
+                HDP_CUDA_TRY(cudaMemcpyAsync(L.net.win_day, net.win_day.data(), sizeof(int) * net.win_day.size(), cudaMemcpyHostToDevice, st));
+                if (net.geo.n_irr) {
+                    HDP_CUDA_TRY(cudaMemcpyAsync(L.net.irr_day, net.irr_day.data(), sizeof(int) * net.irr_day.size(), cudaMemcpyHostToDevice, st));
+                    HDP_CUDA_TRY(cudaMemcpyAsync(L.net.irr_time, net.irr_time.data(), sizeof(int) * net.irr_time.size(), cudaMemcpyHostToDevice, st));
+                }
+            }
+            HDP_CUDA_TRY(cudaMemsetAsync(L.handed_over, 0, sizeof(uint32_t) * (size_t)(1 + blocks), st));
+            const NetHandOver hand{L.handed_over, (int)blocks, geo.n_seg, geo.gc, geo.n_groups, kSegWarps};
+            {
+                KernelTimer timer(kThrNet, st);
+                const int rc = net_launch(net, L.net, x, C, ld_t, d_out, hand, st);
+                if (rc != HDP_B200_OK) return rc;
+            }
+            KernelTimer timer(kThrSeg, st);
+            const unsigned turns = (unsigned)std::min<int64_t>(blocks, 2 * 148 * 4);
+            k_thr_seg<<<turns, kSegWarps * 32, smem, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel, P,
+                                                           (int)b, n_doy, d_out, L.handed_over, (int)blocks);
+            HDP_LAUNCH_CHECK();
+            return HDP_B200_OK;
+        }
         if (geo.cand_m > 0 && g_seg_light && (size_t)blocks <= L.handed_over_count) {
             // high quantiles: the light kernel first, then k_thr_seg for the warps it handed over (non-finite samples,
             // more than kLCap candidates), a small grid taking the blocks on the hand-over list in turns
@@ -1878,7 +1933,10 @@ using namespace hdp;
 
 extern "C" {
 
-void hdp_b200_thresholds_force_generic(int on) { g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; g_seg_light = on != 4; }
+void hdp_b200_thresholds_force_generic(int on)
+{
+    g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; g_seg_light = on != 4; g_net = on != 5;
+}
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                                            int n_doy, int n_y, int W, int P)

@@ -78,11 +78,13 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
                         double *d_out,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
-/* Test hook: which kernel hdp_b200_thresholds uses.  0 = default (k_thr_seg with its candidate filter where the tables
- * allow - for high quantiles in its light variant k_thr_cand, with k_thr_seg behind it for the warps that one hands over -
- * else k_thr_ranked, else k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled any
- * number of times); 2 = k_thr_ranked instead of k_thr_seg; 3 = k_thr_seg without the candidate filter; 4 = k_thr_seg with
- * the candidate filter but without k_thr_cand. */
+/* Test hook: which kernel hdp_b200_thresholds uses.  0 = default (k_thr_net, the lane-per-cell network kernel, where the
+ * tables and quantiles allow - high quantiles, windows of consecutive rows, at most 32 samples per row - with k_thr_seg
+ * behind it for cells with NaN / inf samples; else k_thr_seg with its candidate filter - for high quantiles in its light
+ * variant k_thr_cand, with k_thr_seg behind it for the warps that one hands over - else k_thr_ranked, else
+ * k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled any number of times);
+ * 2 = k_thr_ranked instead of the segment kernels; 3 = k_thr_seg without the candidate filter; 4 = k_thr_seg with the
+ * candidate filter but without k_thr_cand; 5 = the default without k_thr_net. */
 void hdp_b200_thresholds_force_generic(int on);
 
 /* Host-buffer variant (chunked H2D / kernels / D2H pipeline, see csrc/host.cu).  d_keep: optional DEVICE buffer

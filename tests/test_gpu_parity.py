@@ -32,12 +32,13 @@ def ref_layout(out_u16):
 
 
 # ------------------------------------------------------------------------------------------ path 1
-@pytest.fixture(params=["seg", "seg_all", "seg_heavy", "ranked", "generic"])
+@pytest.fixture(params=["default", "cand", "seg_all", "seg_heavy", "ranked", "generic"])
 def thr_path(request, core):
-    """Every threshold path: k_thr_seg with and without its candidate filter, k_thr_ranked, and the generic gather+sort
-    fallback."""
+    """Every threshold path: the default (k_thr_net where the tables and quantiles allow, else the segment kernels), the
+    segment kernels without k_thr_net (k_thr_cand + k_thr_seg), k_thr_seg with and without its candidate filter,
+    k_thr_ranked, and the generic gather+sort fallback."""
     from hdp_b200 import _lib
-    _lib.lib().hdp_b200_thresholds_force_generic({"seg": 0, "generic": 1, "ranked": 2, "seg_all": 3, "seg_heavy": 4}[request.param])
+    _lib.lib().hdp_b200_thresholds_force_generic({"default": 0, "generic": 1, "ranked": 2, "seg_all": 3, "seg_heavy": 4, "cand": 5}[request.param])
     yield request.param
     _lib.lib().hdp_b200_thresholds_force_generic(0)
 
@@ -155,6 +156,89 @@ def test_thresholds_many_handed_over_segments(core):
     assert bits_equal(got[sel], want)
     # NaN rows exactly where a window holds the cell's NaN; every cell without one is finite
     assert np.isfinite(got[1::2]).all()
+
+
+def _net_launches(core, fn):
+    """Runs fn() and returns the names of the threshold kernels it launched."""
+    core.timing_enable(True)
+    core.timing_read()
+    try:
+        fn()
+    finally:
+        names = [n for n, _ in core.timing_read()]
+        core.timing_enable(False)
+    return names
+
+
+@pytest.mark.parametrize("calendar,years,radius,q,C", [
+    ("noleap", 30, 7, np.arange(0.9, 1.0, 0.01), 203),                 # the bench shape: NY = 30, K = 48, three blocks per window
+    ("noleap", 30, 7, np.array([0.95, 1.0]), 64),                      # the maximum (q == 1) beside an interpolated position
+    ("noleap", 11, 7, np.array([0.8, 0.9, 0.999]), 97),                # short rows (NY = 32 with pads), K = 48 of 165
+    ("standard", 12, 7, np.arange(0.9, 1.0, 0.01), 70),                # leap calendar: 366 rows, -1 pads in the last row
+    ("360_day", 20, 2, np.array([0.9, 0.95, 0.97]), 45),               # W = 5: one block per window
+    ("noleap", 24, 4, np.array([0.85, 0.9, 0.99]), 33),                # W = 9: three blocks of three rows
+    ("noleap", 32, 1, np.array([0.6, 0.9]), 40),                       # W = 3: blocks of one row
+    ("noleap", 9, 0, np.array([0.5, 0.9]), 40),                        # W = 1: a window is one row
+    ("all_leap", 16, 3, np.array([0.75, 0.9]), 50),                    # W = 7, 366-day years
+])
+def test_thresholds_network_kernel(core, calendar, years, radius, q, C):
+    # k_thr_net (lane = cell, sorting / merge networks): regular windows through the block decomposition, the mirrored year-end
+    # days row by row, ragged tiles, several chunks per tile, ties / constants / trends, and cells with NaN / +-inf samples
+    # that it must hand to k_thr_seg.  Bit-exact against the oracle, and identical to the segment kernels.
+    from hdp_b200 import _lib, _tables as tb
+    rng = np.random.default_rng(101 + years)
+    end = f"{1960 + years}-12-30" if calendar == "360_day" else f"{1960 + years}-12-31"
+    ax = tb.TimeAxis.date_range("1961-01-01", end, calendar)
+    wt = tb.window_tables(ax.dayofyr, radius)
+    T = len(ax)
+    doy = ax.dayofyr[:, None]
+    x = (15 + 12 * np.sin(2 * np.pi * (doy - 110) / 365) + 3 * rng.standard_normal((T, C))).astype(np.float32)
+    x[:, 0] = np.round(x[:, 0])                               # heavy ties
+    x[:, 1] = 2.5                                             # constant
+    x[:, 2] = np.arange(T, dtype=np.float32) * np.float32(1e-3)   # a trend: one row holds every window's top
+    x[:, 3] = -np.arange(T, dtype=np.float32)
+    x[T // 2, 4] = 3e38                                       # near the pad value's magnitude
+    x[:, 5] = -3.402823466e+38                                # samples EQUAL to the kernel's pad value
+    x[:, 6] = np.where(rng.random(T) < 0.3, 99.0, x[:, 6])    # ties inside the top
+    x[rng.integers(0, T, 3), 11] = np.nan
+    x[rng.integers(0, T, 3), 12] = np.inf
+    x[rng.integers(0, T, 3), 13] = -np.inf
+    x[T - 1, 14] = np.nan                                     # the sample every -1 pad reads
+    x[0, C - 1] = np.inf                                      # last cell of a ragged tile
+    want = oracle.thresholds_batch(x, wt.window_samples(), q)
+    _lib.lib().hdp_b200_thresholds_force_generic(0)
+    names = _net_launches(core, lambda: core.thresholds_array(dev(x), wt, q))
+    assert "k_thr_net" in names, names
+    got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
+    assert bits_equal(got, want)
+    xt = dev(x.T.copy()).t()                                  # time-contiguous input: transposed on the device first
+    assert bits_equal(core.thresholds_array(xt, wt, q).cpu().numpy(), want)
+    _lib.lib().hdp_b200_thresholds_force_generic(5)
+    try:
+        names = _net_launches(core, lambda: core.thresholds_array(dev(x), wt, q))
+        assert "k_thr_net" not in names
+        assert bits_equal(core.thresholds_array(dev(x), wt, q).cpu().numpy(), want)
+    finally:
+        _lib.lib().hdp_b200_thresholds_force_generic(0)
+
+
+def test_thresholds_network_kernel_many_tiles_and_bad_cells(core):
+    # thousands of cells, every third one with a NaN / an infinity somewhere: k_thr_net marks them and k_thr_seg's small grid
+    # works through more hand-over entries than it has blocks; all other cells stay on the network kernel
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(67)
+    ax = tb.TimeAxis.date_range("1961-01-01", "1990-12-31", "noleap")
+    wt = tb.window_tables(ax.dayofyr, 7)
+    T, C = len(ax), 9001
+    x = (15 + 12 * np.sin(2 * np.pi * (ax.dayofyr[:, None] - 110) / 365) + 3 * rng.standard_normal((T, C), dtype=np.float32)).astype(np.float32)
+    bad = np.arange(0, C, 3)
+    x[rng.integers(0, T, bad.size), bad] = np.where(rng.random(bad.size) < 0.5, np.nan, -np.inf).astype(np.float32)
+    q = np.arange(0.9, 1.0, 0.01)
+    got = core.thresholds_array(dev(x), wt, q).cpu().numpy()
+    sel = np.unique(np.concatenate([np.arange(0, 96), rng.integers(0, C, 160), [C - 2, C - 1]]))
+    want = oracle.thresholds_batch(np.ascontiguousarray(x[:, sel]), wt.window_samples(), q)
+    assert bits_equal(got[sel], want)
+    assert np.isfinite(got[1::3]).all() and np.isfinite(got[2::3]).all()
 
 
 def test_thresholds_errors(core):

@@ -44,21 +44,38 @@ namespace hdp {
 #define HDP_NET_PAD (-3.402823466e+38f)
 
 struct NetStepDesc {            // what one row step does besides "order the row and merge it into the running list" (warp-uniform)
-    int reset;                  // the running list starts over with this row
+    int start;                  // the running list starts over: -1 = no, kStartEmpty = with this row alone, else = from that slot
     int other;                  // slot of the stored list to combine the running list with (-1: none)
     int store_dst;              // slot that receives the combination (-1: none)
     int store_run;              // slot that receives the running list itself (-1: none)
-    int emit_day;               // day of year whose thresholds the combination yields (-1: none)
-    int emit_slot;              // scratch slot for the rank lookup
+    int emit_day;               // day of year whose thresholds this step yields (-1: none) - from the combination if `other` >= 0,
+    int emit_slot;              // else from the running list; scratch slot for the rank lookup
 };
+constexpr int kStartEmpty = 1 << 20;
 
+// The row's time indices are warp-uniform: lane y fetches entry y (ONE coalesced load per row, issued two rows ahead) and the
+// data loads of the next row take them by shuffle - no load depends on a load that was issued in the same row step.
 template <int NY>
-__device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *xc, int64_t ld_t, const int *__restrict__ tt)
+__device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *xc, int64_t ld_t, int t_mine)
 {
 #pragma unroll
     for (int y = 0; y < NY; y++) {
-        const int t = __ldg(tt + y);                              // warp-uniform
+        const int t = __shfl_sync(0xffffffffu, t_mine, y);
         raw[y] = t >= 0 ? __ldg(xc + (int64_t)t * ld_t) : HDP_NET_PAD;
+    }
+}
+
+// The requested ranks of a finished window: the list goes through a scratch slot (the positions are run-time values).
+template <int K>
+__device__ __forceinline__ void net_emit(const float (&list)[K], float *o, bool valid, double *dst, int P, const NetSel &sel)
+{
+#pragma unroll
+    for (int e = 0; e < K; e++) o[e * 32] = list[e];
+    if (!valid) return;
+    for (int p = 0; p < P; p++) {
+        const double lower = (double)o[sel.idx_lo[p] * 32], upper = (double)o[sel.idx_hi[p] * 32];
+        // numba/np/arraymath.py:1697-1701 (separately rounded), :1669-1675 for q == 1
+        dst[p] = sel.is_max[p] ? upper : __dadd_rn(__dmul_rn(lower, sel.w_lo[p]), __dmul_rn(upper, sel.w_hi[p]));
     }
 }
 
@@ -68,9 +85,9 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
           const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
           const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
 {
+    static_assert(NY <= 32, "one lane per time index of a row");
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x;
-    const float ninf = HDP_NET_PAD;
     const int64_t n_regular = g.n_tiles * g.n_chunks;
     const int64_t item = blockIdx.x;
     const bool irregular = item >= n_regular;
@@ -82,12 +99,14 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
     float *my = sm + lane;                                        // element e of slot j: my[(j * K + e) * 32]
     const int s = g.s;
     constexpr int kPro = M == 3 ? 2 : 0;                          // prologue blocks of a chunk (the two full blocks after its first one)
-    const int slot_f = s;                                         // M == 3: slot 0 = the pair of full blocks, slots 1..s-1 = suffix lists, slot s = last full block
+    const int slot_f = s;                                         // M == 3: slot 0 = the pair of full blocks, 1..s-1 = suffix lists, s = last full block
+    const int ty = lane < NY ? lane : NY - 1;
 
     const int b0 = chunk * g.steps_per_chunk, b1 = min(b0 + g.steps_per_chunk, g.n_steps);
     const int n_rows = irregular ? g.n_irr * g.W : (kPro + 2 * (b1 - b0)) * s;
+    const int per = irregular ? g.W : s;
 
-    // (pb, it): block phase and row inside it; the row table of step (pb, it)
+    // the row table of step n = (pb, it): block phase and row inside it
     auto row_table = [&](int n, int pb, int it) -> const int * {
         if (irregular) return irr_time + (size_t)n * NY;
         int row;
@@ -98,16 +117,24 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
         }
         return seq_time + (size_t)min(row, g.n_seq) * NY;        // rows past the sequence: the all-pad row
     };
+    auto advance = [&](int &pb, int &it) { if (++it == per) { it = 0; pb++; } };
 
     float raw[NY];
     float run[K];
     float bad_acc = 0.0f;
-    if (n_rows > 0) net_issue_loads<NY>(raw, xc, ld_t, row_table(0, 0, 0));
-#pragma unroll
-    for (int e = 0; e < K; e++) run[e] = ninf;
-
     int pb = 0, it = 0;                                           // irregular items: pb = day, it = row of its window
-    const int per = irregular ? g.W : s;
+    int pb1 = 0, it1 = 0, pb2, it2;                               // steps n + 1 and n + 2
+    int t_next = 0;                                               // time indices of row n + 1 (entry `lane`)
+    if (n_rows > 0) {
+        net_issue_loads<NY>(raw, xc, ld_t, __ldg(row_table(0, 0, 0) + ty));
+        advance(pb1, it1);
+        if (n_rows > 1) t_next = __ldg(row_table(1, pb1, it1) + ty);
+    }
+    pb2 = pb1; it2 = it1;
+    advance(pb2, it2);
+#pragma unroll
+    for (int e = 0; e < K; e++) run[e] = HDP_NET_PAD;
+
     for (int n = 0; n < n_rows; n++) {
         float v[NY];
 #pragma unroll
@@ -115,12 +142,11 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
             v[y] = raw[y];
             bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);             // non-finite census on the otherwise idle FMA pipe: NaN or +-inf -> NaN
         }
-        int pb_n = pb, it_n = it + 1;
-        if (it_n == per) { it_n = 0; pb_n++; }
-        if (n + 1 < n_rows) net_issue_loads<NY>(raw, xc, ld_t, row_table(n + 1, pb_n, it_n));   // in flight while this row is worked on
+        if (n + 1 < n_rows) net_issue_loads<NY>(raw, xc, ld_t, t_next);              // row n + 1: in flight while this row is worked on
+        if (n + 2 < n_rows) t_next = __ldg(row_table(n + 2, pb2, it2) + ty);         // its indices were fetched a row earlier
 
         // ---- what this step does
-        NetStepDesc d{it == 0, -1, -1, -1, -1, 0};
+        NetStepDesc d{it == 0 ? kStartEmpty : -1, -1, -1, -1, -1, 0};
         if (irregular) {
             if (it == per - 1) d.emit_day = irr_day[pb];
         } else if (pb < kPro) {
@@ -130,14 +156,15 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
             }
         } else {
             const int q = pb - kPro, b = b0 + (q >> 1);
-            if (!(q & 1)) {                                       // suffix lists of block b, last row first
-                const int i = s - 1 - it;
-                if (M == 3) d.other = 0;
-                if (i > 0) { if (M == 3) d.store_dst = i; else d.store_run = i; }
-                else { d.emit_day = win_day[b * s]; d.emit_slot = 0; if (d.emit_day < 0) d.other = -1; }
+            if (!(q & 1)) {                                       // block b, last row first: suffix lists, seeded with the two full blocks
+                const int i = s - 1 - it;                         //   behind it (M == 3) so that no extra merge is needed per window
+                if (M == 3 && it == 0) d.start = 0;
+                if (i > 0) d.store_run = i;
+                else d.emit_day = win_day[b * s];
             } else if (it < s - 1) {                              // prefix lists of block b + M: window (b, it + 1)
                 d.emit_day = win_day[b * s + it + 1];
-                if (d.emit_day >= 0) { d.other = it + 1; d.emit_slot = it + 1; }
+                d.emit_slot = it + 1;
+                if (d.emit_day >= 0) d.other = it + 1;
             } else if (M == 3) {                                  // block b + 3 is complete: next pair of full blocks
                 d.other = slot_f; d.store_dst = 0; d.store_run = slot_f;
             }
@@ -145,50 +172,42 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
 
         // ---- order the row, merge it into the running list
         net::Sort<NY>::run(v);
-        if (d.reset) {
+        if (d.start == kStartEmpty) {
 #pragma unroll
-            for (int e = 0; e < K; e++) run[e] = e < NY ? v[e < NY ? e : 0] : ninf;
+            for (int e = 0; e < K; e++) run[e] = e < NY ? v[e < NY ? e : 0] : HDP_NET_PAD;
         } else {
+            if (d.start >= 0) {
+                const float *o = my + (size_t)d.start * K * 32;
+#pragma unroll
+                for (int e = 0; e < K; e++) run[e] = o[e * 32];
+            }
             net::Merge<K, NY>::run(run, v);
         }
 
-        // ---- combine with a stored list, store / look up the requested ranks
-        if (d.other >= 0 || d.emit_day >= 0) {
+        // ---- combine with a stored list; store; look up the requested ranks
+        double *dst = out + ((size_t)(valid ? c : 0) * g.n_doy + max(d.emit_day, 0)) * g.P;
+        if (d.other >= 0) {
             float tmp[K];
-            if (d.other >= 0) {
-                const float *o = my + (size_t)d.other * K * 32;
+            const float *o = my + (size_t)d.other * K * 32;
 #pragma unroll
-                for (int e = 0; e < K; e++) tmp[e] = o[e * 32];
-                net::Merge<K, K>::run(tmp, run);
-            } else {
-#pragma unroll
-                for (int e = 0; e < K; e++) tmp[e] = run[e];
-            }
+            for (int e = 0; e < K; e++) tmp[e] = o[e * 32];
+            net::Merge<K, K>::run(tmp, run);
             if (d.store_dst >= 0) {
-                float *o = my + (size_t)d.store_dst * K * 32;
+                float *w = my + (size_t)d.store_dst * K * 32;
 #pragma unroll
-                for (int e = 0; e < K; e++) o[e * 32] = tmp[e];
+                for (int e = 0; e < K; e++) w[e * 32] = tmp[e];
             }
-            if (d.emit_day >= 0) {
-                float *o = my + (size_t)d.emit_slot * K * 32;
-#pragma unroll
-                for (int e = 0; e < K; e++) o[e * 32] = tmp[e];
-                if (valid) {
-                    double *dst = out + ((size_t)c * g.n_doy + d.emit_day) * g.P;
-                    for (int p = 0; p < g.P; p++) {
-                        const double lower = (double)o[sel.idx_lo[p] * 32], upper = (double)o[sel.idx_hi[p] * 32];
-                        // numba/np/arraymath.py:1697-1701 (separately rounded), :1669-1675 for q == 1
-                        dst[p] = sel.is_max[p] ? upper : __dadd_rn(__dmul_rn(lower, sel.w_lo[p]), __dmul_rn(upper, sel.w_hi[p]));
-                    }
-                }
-            }
+            if (d.emit_day >= 0) net_emit<K>(tmp, my + (size_t)d.emit_slot * K * 32, valid, dst, g.P, sel);
+        } else if (d.emit_day >= 0) {
+            net_emit<K>(run, my + (size_t)d.emit_slot * K * 32, valid, dst, g.P, sel);
         }
         if (d.store_run >= 0) {
-            float *o = my + (size_t)d.store_run * K * 32;
+            float *w = my + (size_t)d.store_run * K * 32;
 #pragma unroll
-            for (int e = 0; e < K; e++) o[e * 32] = run[e];
+            for (int e = 0; e < K; e++) w[e * 32] = run[e];
         }
-        pb = pb_n; it = it_n;
+        pb = pb1; it = it1; pb1 = pb2; it1 = it2;
+        advance(pb2, it2);
     }
 
     // ---- cells with NaN / +-inf samples: all their segments go onto k_thr_seg's hand-over list (it runs behind this kernel)

@@ -78,6 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = _common_deps()
     todo = [s for s in sources() if force or _stale(_obj_of(s), [s] + common)]
     extra = ["-Xptxas=-v"] if verbose else []
+    if os.environ.get("HDP_B200_NET_DEV"):            # kernel iterations: only four instances of k_thr_net (thr_net.cu) instead of 64
+        extra.append("-DHDP_NET_DEV")
     cmds = [[nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", "-o", _obj_of(s), s] for s in todo]
     with ThreadPoolExecutor(max(1, min(len(cmds), os.cpu_count() or 1))) as pool:
         list(pool.map(lambda c: _run(c, verbose), cmds))

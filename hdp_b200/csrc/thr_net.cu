@@ -30,10 +30,15 @@
 // Template instances that exist (samples per row NY x list length K x blocks per window M).  net_plan picks the smallest
 // NY >= n_y (30 exactly for 30-year baselines) and the smallest K >= the deepest requested position; every combination of the
 // two menus must be listed.
-#ifndef HDP_NET_FULL
+#ifdef HDP_NET_DEV                       /* quick kernel iterations: the bench shape and one padded shape */
 #define HDP_NET_NY_MENU 32
 #define HDP_NET_K_MENU 48
 #define HDP_NET_INSTANCES(X) X(30, 48, 3) X(30, 48, 1) X(32, 48, 3) X(32, 48, 1)
+#else
+#define HDP_NET_NY_MENU 8, 16, 32
+#define HDP_NET_K_MENU 16, 32, 48, 64
+#define HDP_NET_ROW(X, ny) X(ny, 16, 3) X(ny, 16, 1) X(ny, 32, 3) X(ny, 32, 1) X(ny, 48, 3) X(ny, 48, 1) X(ny, 64, 3) X(ny, 64, 1)
+#define HDP_NET_INSTANCES(X) HDP_NET_ROW(X, 8) HDP_NET_ROW(X, 16) HDP_NET_ROW(X, 30) HDP_NET_ROW(X, 32)
 #endif
 
 namespace hdp {
@@ -55,13 +60,23 @@ constexpr int kStartEmpty = 1 << 20;
 
 // The row's time indices are warp-uniform: lane y fetches entry y (ONE coalesced load per row, issued two rows ahead) and the
 // data loads of the next row take them by shuffle - no load depends on a load that was issued in the same row step.
-template <int NY>
-__device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *xc, int64_t ld_t, int t_mine)
+// `pitch` = bytes between consecutive time steps (< 4 GB): the address is base + t * pitch, ONE 32 x 32 -> 64 bit multiply-add.
+// kPads: rows are shorter than NY (entries -1); a row past the end of the sequence is all pads and skipped as a whole.
+template <int NY, bool kPads>
+__device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *xc, uint32_t pitch, int t_mine)
 {
+    const int t0 = __shfl_sync(0xffffffffu, t_mine, 0);
+    if (t0 < 0) {                                                 // warp-uniform: entry 0 is a pad only in the all-pad row
+#pragma unroll
+        for (int y = 0; y < NY; y++) raw[y] = HDP_NET_PAD;
+        return;
+    }
 #pragma unroll
     for (int y = 0; y < NY; y++) {
-        const int t = __shfl_sync(0xffffffffu, t_mine, y);
-        raw[y] = t >= 0 ? __ldg(xc + (int64_t)t * ld_t) : HDP_NET_PAD;
+        const int t = y ? __shfl_sync(0xffffffffu, t_mine, y) : t0;
+        const float *p = (const float *)((const char *)xc + (uint64_t)(uint32_t)t * pitch);
+        if (kPads) raw[y] = t >= 0 ? __ldg(p) : HDP_NET_PAD;
+        else raw[y] = __ldg(p);
     }
 }
 
@@ -79,9 +94,9 @@ __device__ __forceinline__ void net_emit(const float (&list)[K], float *o, bool 
     }
 }
 
-template <int NY, int K, int M>
+template <int NY, int K, int M, bool kPads>
 __global__ void __launch_bounds__(32)
-k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
+k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
           const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
           const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
 {
@@ -126,7 +141,7 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
     int pb1 = 0, it1 = 0, pb2, it2;                               // steps n + 1 and n + 2
     int t_next = 0;                                               // time indices of row n + 1 (entry `lane`)
     if (n_rows > 0) {
-        net_issue_loads<NY>(raw, xc, ld_t, __ldg(row_table(0, 0, 0) + ty));
+        net_issue_loads<NY, kPads>(raw, xc, ld_t, __ldg(row_table(0, 0, 0) + ty));
         advance(pb1, it1);
         if (n_rows > 1) t_next = __ldg(row_table(1, pb1, it1) + ty);
     }
@@ -142,7 +157,7 @@ k_thr_net(const float *__restrict__ x, int64_t C, int64_t ld_t,
             v[y] = raw[y];
             bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);             // non-finite census on the otherwise idle FMA pipe: NaN or +-inf -> NaN
         }
-        if (n + 1 < n_rows) net_issue_loads<NY>(raw, xc, ld_t, t_next);              // row n + 1: in flight while this row is worked on
+        if (n + 1 < n_rows) net_issue_loads<NY, kPads>(raw, xc, ld_t, t_next);              // row n + 1: in flight while this row is worked on
         if (n + 2 < n_rows) t_next = __ldg(row_table(n + 2, pb2, it2) + ty);         // its indices were fetched a row earlier
 
         // ---- what this step does
@@ -311,15 +326,16 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
     pl.usable = true;
 }
 
-template <int NY, int K, int M>
+template <int NY, int K, int M, bool kPads>
 static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out,
                         const NetHandOver &hand, cudaStream_t st)
 {
     const NetGeom &g = pl.geo;
-    HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net<NY, K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net<NY, K, M, kPads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
-    if (items > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
-    k_thr_net<NY, K, M><<<(unsigned)items, 32, g.smem, st>>>(x, C, ld_t, tb.seq_time, tb.win_day, tb.irr_day, tb.irr_time, g, pl.sel, out, hand);
+    if (items > 0x7fffffffLL || ld_t <= 0 || ld_t >= (1LL << 30)) return HDP_B200_ERR_UNSUPPORTED;
+    k_thr_net<NY, K, M, kPads><<<(unsigned)items, 32, g.smem, st>>>(x, C, (uint32_t)(ld_t * sizeof(float)), tb.seq_time, tb.win_day, tb.irr_day,
+                                                                     tb.irr_time, g, pl.sel, out, hand);
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;
 }
@@ -327,7 +343,10 @@ static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, 
 int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st)
 {
     const NetGeom &g = pl.geo;
-#define HDP_NET_CASE(ny, k, m) if (g.NY == ny && g.K == k && g.M == m) return net_launch_t<ny, k, m>(pl, tb, x, C, ld_t, out, hand, st);
+#define HDP_NET_CASE(ny, k, m)                                                                             \
+    if (g.NY == ny && g.K == k && g.M == m)                                                                \
+        return g.n_y == ny ? net_launch_t<ny, k, m, false>(pl, tb, x, C, ld_t, out, hand, st)              \
+                           : net_launch_t<ny, k, m, true>(pl, tb, x, C, ld_t, out, hand, st);
     HDP_NET_INSTANCES(HDP_NET_CASE)
 #undef HDP_NET_CASE
     return HDP_B200_ERR_UNSUPPORTED;

@@ -180,6 +180,8 @@ def _net_launches(core, fn):
     ("noleap", 32, 1, np.array([0.6, 0.9]), 40),                       # W = 3: blocks of one row
     ("noleap", 9, 0, np.array([0.5, 0.9]), 40),                        # W = 1: a window is one row
     ("all_leap", 16, 3, np.array([0.75, 0.9]), 50),                    # W = 7, 366-day years
+    ("noleap", 30, 10, np.array([0.9, 0.95]), 70),                     # W = 21: blocks of seven rows, K = 64
+    ("noleap", 6, 7, np.array([0.9, 0.99]), 40),                       # NY = 8, K = 16
 ])
 def test_thresholds_network_kernel(core, calendar, years, radius, q, C):
     # k_thr_net (lane = cell, sorting / merge networks): regular windows through the block decomposition, the mirrored year-end

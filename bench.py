@@ -390,16 +390,18 @@ class Job:
 
     # ---- the output gather: every measure's thresholds and metrics of all ranks, over NCCL (NVLink / NVSwitch)
     def gather_once(self):
+        """Every rank's outputs side by side on every rank (rank-major shards: what a consumer that assembles the arrays on the
+        host needs; shard.gather_cells would add a device repacking pass for the cell-minor metrics)."""
         sh = self.shard
         got = 0
         for m in range(self.M):
             if not self.shared_thr:
-                t = sh.gather_cells(self.thr[m], self.C_global, dim=0)
-                got += t.numel() * 8
+                t, _ = sh.gather_shards(self.thr[m], self.C_global, dim=0)
+                got += t.numel() * t.element_size()
                 del t
             if self.out[m] is not None:
-                o = sh.gather_cells(self.out[m], self.C_global, dim=-1)
-                got += o.numel() * 2
+                o, _ = sh.gather_shards(self.out[m], self.C_global, dim=-1)
+                got += o.numel() * o.element_size()
                 del o
         return got
 
@@ -468,7 +470,7 @@ def timed_gather(job, reps, world, dev):
     ms = float(t.item())
     received = total * (world - 1) / world
     return {"ms_per_step": ms, "bytes_gathered_per_step": int(total), "bytes_received_per_rank": int(received),
-            "nvlink_ingress_gbs_per_gpu": received / (ms / 1e3) / 1e9, "collective": "all_gather (NCCL) of thresholds f64 + metrics u16",
+            "nvlink_ingress_gbs_per_gpu": received / (ms / 1e3) / 1e9, "collective": "all_gather (NCCL) of thresholds f64 + metrics u16 (shard.gather_shards: rank-major shards, no repacking pass)",
             "reps": reps}
 
 

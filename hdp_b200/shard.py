@@ -103,6 +103,43 @@ def gather_cells(local, n_cells: int, dim: int = -1, group=None, align: int = CE
     return torch.cat(parts, dim=0).movedim(0, dim)
 
 
+def gather_shards(local, n_cells: int, dim: int = -1, group=None, align: int = CELL_ALIGN):
+    """The NVLink part of the gather alone: every rank's shard as it lies in memory, side by side in ONE buffer
+    ``[world, widest shard (flattened)]`` plus the cell ranges - no repacking pass on the device.  This is all a consumer
+    needs that assembles the result elsewhere (each shard is a column block ``[..., c0:c1]`` of the full array: a strided
+    device-to-host copy or a view per shard); :func:`gather_cells` adds the repacking into one dense array."""
+    import torch
+    import torch.distributed as dist
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    ranges = all_ranges(n_cells, world, align)
+    dim = dim % local.dim()
+    if local.shape[dim] != ranges[rank][1] - ranges[rank][0]:
+        raise ValueError(f"rank {rank} holds {local.shape[dim]} cells, expected {ranges[rank][1] - ranges[rank][0]}")
+    flat = local.contiguous().reshape(-1)
+    as_bytes = flat.view(torch.uint8) if flat.dtype == torch.uint16 else flat          # NCCL/gloo have no uint16 type
+    per_cell = as_bytes.numel() // max(local.shape[dim], 1) if local.shape[dim] else 0
+    if not local.shape[dim]:                                                            # empty shard: derive the size from the shape
+        per_cell = (2 if local.dtype == torch.uint16 else 1)
+        for i, n in enumerate(local.shape):
+            if i != dim:
+                per_cell *= int(n)
+    widest = max(b - a for a, b in ranges)
+    bucket = torch.empty((world, widest * per_cell), dtype=as_bytes.dtype, device=as_bytes.device)
+    if not multi:
+        bucket[0].copy_(as_bytes)
+        return bucket, ranges
+    if as_bytes.numel() == widest * per_cell:
+        dist.all_gather_into_tensor(bucket.view(-1), as_bytes, group=group)
+    else:
+        mine = torch.zeros(widest * per_cell, dtype=as_bytes.dtype, device=as_bytes.device)
+        mine[: as_bytes.numel()].copy_(as_bytes)
+        dist.all_gather_into_tensor(bucket.view(-1), mine, group=group)
+    return bucket, ranges
+
+
 def member_pieces(c0: int, c1: int, grid_cells: int) -> List[Tuple[int, int, int]]:
     """The flattened (member, grid cell) range ``[c0, c1)`` as ``(member, g0, g1)`` pieces, one per member it touches
     (an ensemble sharded by flattened cell index: every piece meets the member-free thresholds of grid cells g0..g1)."""

@@ -79,6 +79,13 @@ def _worker(rank, world, port, C, result_dir, local=False):
         c0, c1 = shard.cell_range(C, rank, world)
         ids = shard.gather_cells(torch.arange(c0, c1, dtype=torch.int64), C, dim=0)
         assert ids.tolist() == list(range(C))
+        # the rank-major form: every shard as it lies in memory, trimmed by its range
+        local = met[..., c0:c1].contiguous()
+        bucket, ranges = shard.gather_shards(local, C, dim=-1)
+        rows = local.numel() // max(c1 - c0, 1) if c1 > c0 else int(np.prod(met.shape[:-1]))
+        for r, (a, b) in enumerate(ranges):
+            blk = bucket[r, : (b - a) * rows * 2].view(torch.uint16).view(*met.shape[:-1], b - a)
+            assert torch.equal(blk.view(torch.int16), met[..., a:b].contiguous().view(torch.int16))
     finally:
         dist.destroy_process_group()
 

@@ -34,22 +34,15 @@ constexpr int kTileCells = 32;
 constexpr int kTileDoy = 32;
 constexpr int kHotYears = 2;  // words (years) a warp compares against one register copy of the day's thresholds
 constexpr int kFillLoads = 5;  // doubles of the threshold tile a lane has in flight
-constexpr int kHotDays = 8;   // days of each of them whose samples are in flight together (8 or 16)
+constexpr int kHotDays = 16;  // days of each of them whose samples are in flight together
 constexpr int kTilePad = 33;   // [.. ][33]: conflict-free both for the e-major fill and the lane-major reads
 
-// 1.0f where v > t, else 0.0f (false when either side is NaN): ONE instruction on the ALU pipe (FSET.BF)
-__device__ __forceinline__ float gt_as_float(float v, float t)
+// m |= bit where v > t (false when either side is NaN): one compare and one predicated OR with an immediate
+__device__ __forceinline__ void or_if_gt(uint32_t &m, float v, float t, uint32_t bit)
 {
-    float d;
-    asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(v), "f"(t));
-    return d;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(v), "f"(t), "r"(bit));
 }
 
-// kHotDays days of kHotYears words against the days' thresholds.  The hot-day bits of a (word, percentile) are collected in a
-// FLOAT: acc = 2 * acc + (v > t), days taken last to first, so that a comparison costs one FSET on the ALU pipe plus one FFMA
-// with an immediate on the FMA pipe - the two pipes work side by side - instead of two ALU instructions (compare, predicated
-// OR).  kHotDays <= 16 bits are exact in a float; adding 2^23 leaves them in the low mantissa bits, from where one PRMT puts
-// them at the days' place in the word.
 template <int PG, int J0>
 __device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const float *const (&xp)[kHotYears], const int (&jo)[kHotYears],
                                          const int (&nb)[kHotYears], int64_t ld_t, const float *ts)
@@ -60,30 +53,16 @@ __device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const flo
 #pragma unroll
         for (int j = 0; j < kHotDays; j++)                 // NaN = never hot: days outside the word
             v[y][j] = (unsigned)(J0 + j - jo[y]) < (unsigned)nb[y] ? __ldg(xp[y] + (int64_t)(J0 + j) * ld_t) : __int_as_float(0x7fc00000);
-    float acc[kHotYears][PG];
 #pragma unroll
-    for (int y = 0; y < kHotYears; y++)
-#pragma unroll
-        for (int q = 0; q < PG; q++) acc[y][q] = 0.0f;
-#pragma unroll
-    for (int j = kHotDays - 1; j >= 0; j--) {
+    for (int j = 0; j < kHotDays; j++) {
         float t[PG];
 #pragma unroll
         for (int q = 0; q < PG; q++) t[q] = ts[((J0 + j) * PG + q) * kTilePad];
 #pragma unroll
         for (int y = 0; y < kHotYears; y++)
 #pragma unroll
-            for (int q = 0; q < PG; q++) acc[y][q] = __fmaf_rn(acc[y][q], 2.0f, gt_as_float(v[y][j], t[q]));
+            for (int q = 0; q < PG; q++) or_if_gt(m[y][q], v[y][j], t[q], 1u << (J0 + j));
     }
-    static_assert((kHotDays == 16 || kHotDays == 8) && J0 % kHotDays == 0 && J0 < 32, "the PRMT selectors below place whole bytes");
-    // result bytes 3..0 come from m (selectors 3..0) except the days' byte(s), which come from the float's low bytes (4, 5)
-    constexpr uint32_t sel = kHotDays == 16 ? (J0 == 0 ? 0x3254u : 0x5410u)
-                                            : (J0 == 0 ? 0x3214u : J0 == 8 ? 0x3240u : J0 == 16 ? 0x3410u : 0x4210u);
-#pragma unroll
-    for (int y = 0; y < kHotYears; y++)
-#pragma unroll
-        for (int q = 0; q < PG; q++)
-            m[y][q] = __byte_perm(m[y][q], __float_as_uint(acc[y][q] + 8388608.0f), sel);
 }
 
 template <int PG>
@@ -158,10 +137,6 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
             const float *ts = thr_s + (size_t)(pg / PG) * (kTileDoy * PG * kTilePad) + lane;
             hot_half<PG, 0>(m, xp, jo, nb, ld_t, ts);
             if (j_hi > kHotDays) hot_half<PG, kHotDays>(m, xp, jo, nb, ld_t, ts);      // warp-uniform
-            if (kHotDays == 8) {
-                if (j_hi > 16) hot_half<PG, 16>(m, xp, jo, nb, ld_t, ts);
-                if (j_hi > 24) hot_half<PG, 24>(m, xp, jo, nb, ld_t, ts);
-            }
 #pragma unroll
             for (int y = 0; y < kHotYears; y++)
 #pragma unroll

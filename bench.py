@@ -331,9 +331,13 @@ class Job:
         self.south_np = (lat_local < 0).astype(np.uint8)
 
         def field(axis, seed_of, off, trend, pieces):
-            parts = [synth.gridded_field(lat, axis.dayofyr, seed=seed_of(m), offset=off, trend=trend, device=dev, cols=(g0, g1))
-                     for m, g0, g1 in pieces]
-            return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+            full = torch.empty((len(axis), sum(g1 - g0 for _, g0, g1 in pieces)), dtype=torch.float32, device=dev)
+            a = 0
+            for m, g0, g1 in pieces:                                    # every piece straight into its column block
+                synth.gridded_field(lat, axis.dayofyr, seed=seed_of(m), offset=off, trend=trend, device=dev, cols=(g0, g1),
+                                    out=full[:, a:a + g1 - g0])
+                a += g1 - g0
+            return full
 
         self.base, self.run = [], []
         for i, off in enumerate(offsets):
@@ -704,44 +708,63 @@ def main():
     if not args.no_extra and not args.cells:
         job.free()
         k_steps, k_warm = max(2, args.steps // 3), 3
-        if world > 1 and scaling == "weak" and not wl.members > 1:
+        def guarded(fn):
+            """An extra record must never cost the headline: a failure (e.g. out of memory) is reported in its place.  Failures
+            here are symmetric across ranks (same shapes everywhere), so no rank is left waiting in a collective."""
+            try:
+                return fn()
+            except Exception as e:                         # noqa: BLE001
+                torch.cuda.empty_cache()
+                return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+        def strong_record():
             sj = Job(wl, dev, rank, world, 1)
-            r = timed_steps(sj, k_steps, k_warm, world, dev)
-            rec = sub_record(sj, r, k_steps, peak)
-            rec["sharding"] = f"one grid of {sj.grid} cells cut into {world} contiguous 32-aligned ranges; no collective on the path"
-            if not args.no_gather:
-                rec["gather"] = timed_gather(sj, 2, world, dev)
-            if rank == 0:
-                line["strong"] = rec
-            sj.free()
-        if world >= 4 and wl.name == "cmip6_1deg":
+            try:
+                r = timed_steps(sj, k_steps, k_warm, world, dev)
+                rec = sub_record(sj, r, k_steps, peak)
+                rec["sharding"] = f"one grid of {sj.grid} cells cut into {world} contiguous 32-aligned ranges; no collective on the path"
+                if not args.no_gather:
+                    rec["gather"] = timed_gather(sj, 2, world, dev)
+                return rec
+            finally:
+                sj.free()
+
+        def lens50_record():
             lw = workloads.get("lens50")
             lj = Job(lw, dev, rank, world, 1)
-            r = timed_steps(lj, 2, 2, world, dev)
-            rec = sub_record(lj, r, 2, peak)
-            rec["sharding"] = (f"{lj.members} members x {lj.grid} cells flattened, {world} contiguous ranges ({len(lj.pieces)} member pieces on rank 0); "
-                               "thresholds: 1/N of the grid per rank + one all_gather inside the timed step")
-            rec["imbalance"] = {"cells_per_gpu_max": int(max(b - a for a, b in lj.shard.all_ranges(lj.C_global, world))),
-                                "cells_per_gpu_mean": lj.C_global / world}
-            if not args.no_gather:
-                rec["gather"] = timed_gather(lj, 1, world, dev)
-            if rank == 0:
-                line["lens50"] = rec
-            lj.free()
-        if world == 1 and wl.name == "cmip6_1deg":
-            extra = {}
-            for name in ("lens_member", "wide_sweep", "era5_025deg"):
-                xw = workloads.get(name)
-                xj = Job(xw, dev, rank, world, 1)
+            try:
+                r = timed_steps(lj, 2, 2, world, dev)
+                rec = sub_record(lj, r, 2, peak)
+                rec["sharding"] = (f"{lj.members} members x {lj.grid} cells flattened, {world} contiguous ranges ({len(lj.pieces)} member pieces "
+                                   "on rank 0); thresholds: 1/N of the grid per rank + one all_gather inside the timed step")
+                rec["imbalance"] = {"cells_per_gpu_max": int(max(b - a for a, b in lj.shard.all_ranges(lj.C_global, world))),
+                                    "cells_per_gpu_mean": lj.C_global / world}
+                if not args.no_gather:
+                    rec["gather"] = timed_gather(lj, 1, world, dev)
+                return rec
+            finally:
+                lj.free()
+
+        def config_record(name):
+            xw = workloads.get(name)
+            xj = Job(xw, dev, rank, world, 1)
+            try:
                 r = timed_steps(xj, k_steps, k_warm, world, dev, with_kernels=True)
                 rec = sub_record(xj, r, k_steps, peak)
                 kms, _, _ = kernel_breakdown(r["kern"], k_steps * xj.M)
                 rec["kernel_ms_per_measure"] = kms
                 rec["description"] = xw.description
                 rec["parity_on_sample"] = parity_on_sample(xj, 16, host_cores())
-                extra[name] = rec
+                return rec
+            finally:
                 xj.free()
-            line["configs"] = extra
+
+        if world > 1 and scaling == "weak" and not wl.members > 1:
+            line["strong"] = guarded(strong_record)
+        if world >= 4 and wl.name == "cmip6_1deg":
+            line["lens50"] = guarded(lens50_record)
+        if world == 1 and wl.name == "cmip6_1deg":
+            line["configs"] = {name: guarded(lambda name=name: config_record(name)) for name in ("lens_member", "wide_sweep", "era5_025deg")}
 
     if rank == 0:
         emit(line)

@@ -69,14 +69,15 @@ def grid_latitudes(n_lat: int, n_lon: int) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.0, offset: float = 0.0,
-                  sigma: float = 3.0, ar: float = 0.7, device="cuda", chunk_days: int = 2048, cols=None):
+                  sigma: float = 3.0, ar: float = 0.7, device="cuda", chunk_days: int = 2048, cols=None, out=None):
     """float32 ``[T, C]`` on ``device``:
     ``15 + offset + 12 cos(lat) sin(2 pi (doy-110)/365) sgn(lat) - 25 |lat|/90 + trend t/T + sigma AR(1)``.
 
     The AR(1) term is the stationary filter ``sqrt(1-ar^2) * sum_k ar^k e[t-k]`` truncated at 32 lags
     (ar^32 ~ 1e-5), so every time chunk can be generated independently and reproducibly from the seed.
     ``cols = (g0, g1)`` keeps only cells g0..g1 of the field (a shard): the values are those of the full field, whoever
-    generates them, because the noise is always drawn for the whole grid.
+    generates them, because the noise is always drawn for the whole grid.  ``out``: optional ``[T, g1 - g0]`` float32
+    tensor (any strides, e.g. a column block of a larger array) that receives the field.
     """
     import torch
     dev = torch.device(device)
@@ -87,7 +88,10 @@ def gridded_field(cell_lat, dayofyr: np.ndarray, *, seed: int, trend: float = 0.
     amp = 12.0 * torch.cos(torch.deg2rad(lat)) * torch.where(lat < 0, -1.0, 1.0)
     base = 15.0 + offset - 25.0 * lat.abs() / 90.0
     g0, g1 = (0, C) if cols is None else (int(cols[0]), int(cols[1]))
-    out = torch.empty((T, g1 - g0), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((T, g1 - g0), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (T, g1 - g0) or out.dtype != torch.float32:
+        raise ValueError("out must be float32 [T, cells]")
     lags = 32
     w = (ar ** torch.arange(lags, device=dev, dtype=torch.float32)) * float(np.sqrt(1 - ar * ar)) * sigma
     for t0 in range(0, T, chunk_days):

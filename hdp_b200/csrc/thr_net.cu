@@ -54,8 +54,7 @@ struct NetStepDesc {            // what one row step does besides "order the row
     int store_dst;              // slot that receives the combination (-1: none)
     int store_run;              // slot that receives the running list itself (-1: none)
     int emit_day;               // day of year whose thresholds this step yields (-1: none) - from the combination if `other` >= 0,
-    int emit_slot;              // else from the running list; scratch slot for the rank lookup
-};
+};                              // else from the running list.  (The rank lookup goes through slot 0, which is free whenever a window ends.)
 constexpr int kStartEmpty = 1 << 20;
 
 // The row's time indices are warp-uniform: lane y fetches entry y (ONE coalesced load per row, issued two rows ahead) and the
@@ -94,27 +93,118 @@ __device__ __forceinline__ void net_emit(const float (&list)[K], float *o, bool 
     }
 }
 
-template <int NY, int K, int M, bool kPads>
-__global__ void __launch_bounds__(32)
-k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
-          const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
-          const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
+// ---- where the lists that outlive a row step wait ----
+// Slot numbers: 0 = the pair of full blocks (M == 3) and the scratch for the rank lookup, 1 .. s-1 = suffix lists, s = last full block.
+template <int K>
+struct SlotsSmem {                                                // every slot in shared memory: element e of slot j at my[(j * K + e) * 32]
+    float *my;
+    __device__ __forceinline__ float *scratch() const { return my; }
+    __device__ __forceinline__ void load(int slot, float (&a)[K]) const
+    {
+        const float *o = my + (size_t)slot * K * 32;
+#pragma unroll
+        for (int e = 0; e < K; e++) a[e] = o[e * 32];
+    }
+    __device__ __forceinline__ void store(int slot, const float (&a)[K]) const
+    {
+        float *w = my + (size_t)slot * K * 32;
+#pragma unroll
+        for (int e = 0; e < K; e++) w[e * 32] = a[e];
+    }
+};
+
+// Tensor memory as list storage.  TMEM is [128 lanes][512 columns] of 32 bits; a warp reaches the 32 lanes of its quarter
+// (warp % 4) with tcgen05.ld / tcgen05.st, thread i <-> lane i, N consecutive columns <-> N registers: exactly the
+// [element][cell] layout of a list, with no address arithmetic per element and none of the shared memory that limits how many
+// warps an SM can hold.  (No tensor-core instruction is involved: the memory is used as a 256 KB scratchpad.)
+#define HDP_R16(a, o) "=f"(a[o]), "=f"(a[o + 1]), "=f"(a[o + 2]), "=f"(a[o + 3]), "=f"(a[o + 4]), "=f"(a[o + 5]), "=f"(a[o + 6]), "=f"(a[o + 7]), \
+                      "=f"(a[o + 8]), "=f"(a[o + 9]), "=f"(a[o + 10]), "=f"(a[o + 11]), "=f"(a[o + 12]), "=f"(a[o + 13]), "=f"(a[o + 14]), "=f"(a[o + 15])
+#define HDP_W16(a, o) "f"(a[o]), "f"(a[o + 1]), "f"(a[o + 2]), "f"(a[o + 3]), "f"(a[o + 4]), "f"(a[o + 5]), "f"(a[o + 6]), "f"(a[o + 7]), \
+                      "f"(a[o + 8]), "f"(a[o + 9]), "f"(a[o + 10]), "f"(a[o + 11]), "f"(a[o + 12]), "f"(a[o + 13]), "f"(a[o + 14]), "f"(a[o + 15])
+#define HDP_RW16(a, o) "+f"(a[o]), "+f"(a[o + 1]), "+f"(a[o + 2]), "+f"(a[o + 3]), "+f"(a[o + 4]), "+f"(a[o + 5]), "+f"(a[o + 6]), "+f"(a[o + 7]), \
+                       "+f"(a[o + 8]), "+f"(a[o + 9]), "+f"(a[o + 10]), "+f"(a[o + 11]), "+f"(a[o + 12]), "+f"(a[o + 13]), "+f"(a[o + 14]), "+f"(a[o + 15])
+
+template <int K, int O>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&a)[K])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : HDP_R16(a, O) : "r"(taddr + O) : "memory");
+}
+template <int K, int O>
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&a)[K])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr + O), HDP_W16(a, O) : "memory");
+}
+// The loaded registers are valid after tcgen05.wait::ld; naming them as in/out operands keeps every use of them behind the wait.
+template <int K, int O>
+__device__ __forceinline__ void tmem_wait_ld16(float (&a)[K])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : HDP_RW16(a, O) :: "memory");
+}
+
+template <int K>
+struct SlotsMixed {                                               // suffix lists 1 .. n_tm in tensor memory, everything else in shared memory
+    float *my;                                                    // shared memory: slot 0, the last full block, suffix lists n_tm + 1 ..
+    uint32_t taddr;                                               // this warp's lanes and first column
+    int n_tm, slot_f;
+    __device__ __forceinline__ float *scratch() const { return my; }
+    __device__ __forceinline__ int smem_index(int slot) const { return slot == 0 ? 0 : slot == slot_f ? 1 : 1 + slot - n_tm; }
+    __device__ __forceinline__ bool in_tmem(int slot) const { return slot >= 1 && slot <= n_tm && slot != slot_f; }
+    __device__ __forceinline__ void load(int slot, float (&a)[K]) const
+    {
+        if (in_tmem(slot)) {                                      // warp-uniform
+            const uint32_t t = taddr + (uint32_t)(slot - 1) * K;
+            tmem_ld16<K, 0>(t, a);
+            if constexpr (K > 16) tmem_ld16<K, 16>(t, a);
+            if constexpr (K > 32) tmem_ld16<K, 32>(t, a);
+            if constexpr (K > 48) tmem_ld16<K, 48>(t, a);
+            tmem_wait_ld16<K, 0>(a);
+            if constexpr (K > 16) tmem_wait_ld16<K, 16>(a);
+            if constexpr (K > 32) tmem_wait_ld16<K, 32>(a);
+            if constexpr (K > 48) tmem_wait_ld16<K, 48>(a);
+        } else {
+            const float *o = my + (size_t)smem_index(slot) * K * 32;
+#pragma unroll
+            for (int e = 0; e < K; e++) a[e] = o[e * 32];
+        }
+    }
+    __device__ __forceinline__ void store(int slot, const float (&a)[K]) const
+    {
+        if (in_tmem(slot)) {
+            const uint32_t t = taddr + (uint32_t)(slot - 1) * K;
+            tmem_st16<K, 0>(t, a);
+            if constexpr (K > 16) tmem_st16<K, 16>(t, a);
+            if constexpr (K > 32) tmem_st16<K, 32>(t, a);
+            if constexpr (K > 48) tmem_st16<K, 48>(t, a);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else {
+            float *w = my + (size_t)smem_index(slot) * K * 32;
+#pragma unroll
+            for (int e = 0; e < K; e++) w[e * 32] = a[e];
+        }
+    }
+};
+
+// One work item = (32-cell tile, chunk of super-steps) or (tile, the irregular days), worked through by ONE warp.
+template <int NY, int K, int M, bool kPads, class Slots>
+__device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const float *__restrict__ x, int64_t C, uint32_t ld_t,
+                                         const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day,
+                                         const int *__restrict__ irr_time, const NetGeom &g, const NetSel &sel, double *__restrict__ out,
+                                         const NetHandOver &hand)
 {
     static_assert(NY <= 32, "one lane per time index of a row");
-    extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int64_t n_regular = g.n_tiles * g.n_chunks;
-    const int64_t item = blockIdx.x;
     const bool irregular = item >= n_regular;
     const int64_t tile = irregular ? item - n_regular : item / g.n_chunks;
     const int chunk = irregular ? 0 : (int)(item - tile * g.n_chunks);
     const int64_t c = tile * 32 + lane;
     const bool valid = c < C;
     const float *xc = x + (valid ? c : C - 1);
-    float *my = sm + lane;                                        // element e of slot j: my[(j * K + e) * 32]
     const int s = g.s;
     constexpr int kPro = M == 3 ? 2 : 0;                          // prologue blocks of a chunk (the two full blocks after its first one)
-    const int slot_f = s;                                         // M == 3: slot 0 = the pair of full blocks, 1..s-1 = suffix lists, s = last full block
+    const int slot_f = s;
     const int ty = lane < NY ? lane : NY - 1;
 
     const int b0 = chunk * g.steps_per_chunk, b1 = min(b0 + g.steps_per_chunk, g.n_steps);
@@ -157,11 +247,11 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
             v[y] = raw[y];
             bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);             // non-finite census on the otherwise idle FMA pipe: NaN or +-inf -> NaN
         }
-        if (n + 1 < n_rows) net_issue_loads<NY, kPads>(raw, xc, ld_t, t_next);              // row n + 1: in flight while this row is worked on
+        if (n + 1 < n_rows) net_issue_loads<NY, kPads>(raw, xc, ld_t, t_next);       // row n + 1: in flight while this row is worked on
         if (n + 2 < n_rows) t_next = __ldg(row_table(n + 2, pb2, it2) + ty);         // its indices were fetched a row earlier
 
         // ---- what this step does
-        NetStepDesc d{it == 0 ? kStartEmpty : -1, -1, -1, -1, -1, 0};
+        NetStepDesc d{it == 0 ? kStartEmpty : -1, -1, -1, -1, -1};
         if (irregular) {
             if (it == per - 1) d.emit_day = irr_day[pb];
         } else if (pb < kPro) {
@@ -178,7 +268,6 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
                 else d.emit_day = win_day[b * s];
             } else if (it < s - 1) {                              // prefix lists of block b + M: window (b, it + 1)
                 d.emit_day = win_day[b * s + it + 1];
-                d.emit_slot = it + 1;
                 if (d.emit_day >= 0) d.other = it + 1;
             } else if (M == 3) {                                  // block b + 3 is complete: next pair of full blocks
                 d.other = slot_f; d.store_dst = 0; d.store_run = slot_f;
@@ -191,11 +280,7 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
 #pragma unroll
             for (int e = 0; e < K; e++) run[e] = e < NY ? v[e < NY ? e : 0] : HDP_NET_PAD;
         } else {
-            if (d.start >= 0) {
-                const float *o = my + (size_t)d.start * K * 32;
-#pragma unroll
-                for (int e = 0; e < K; e++) run[e] = o[e * 32];
-            }
+            if (d.start >= 0) slots.load(d.start, run);
             net::Merge<K, NY>::run(run, v);
         }
 
@@ -203,24 +288,14 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
         double *dst = out + ((size_t)(valid ? c : 0) * g.n_doy + max(d.emit_day, 0)) * g.P;
         if (d.other >= 0) {
             float tmp[K];
-            const float *o = my + (size_t)d.other * K * 32;
-#pragma unroll
-            for (int e = 0; e < K; e++) tmp[e] = o[e * 32];
+            slots.load(d.other, tmp);
             net::Merge<K, K>::run(tmp, run);
-            if (d.store_dst >= 0) {
-                float *w = my + (size_t)d.store_dst * K * 32;
-#pragma unroll
-                for (int e = 0; e < K; e++) w[e * 32] = tmp[e];
-            }
-            if (d.emit_day >= 0) net_emit<K>(tmp, my + (size_t)d.emit_slot * K * 32, valid, dst, g.P, sel);
+            if (d.store_dst >= 0) slots.store(d.store_dst, tmp);
+            if (d.emit_day >= 0) net_emit<K>(tmp, slots.scratch(), valid, dst, g.P, sel);
         } else if (d.emit_day >= 0) {
-            net_emit<K>(run, my + (size_t)d.emit_slot * K * 32, valid, dst, g.P, sel);
+            net_emit<K>(run, slots.scratch(), valid, dst, g.P, sel);
         }
-        if (d.store_run >= 0) {
-            float *w = my + (size_t)d.store_run * K * 32;
-#pragma unroll
-            for (int e = 0; e < K; e++) w[e * 32] = run[e];
-        }
+        if (d.store_run >= 0) slots.store(d.store_run, run);
         pb = pb1; it = it1; pb1 = pb2; it1 = it2;
         advance(pb2, it2);
     }
@@ -234,6 +309,58 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
             if (atomicOr(&hand.list[1 + bid], 1u << w) == 0u) hand.list[1 + hand.n_blocks + atomicAdd(&hand.list[0], 1u)] = bid;
         }
     }
+}
+
+// One warp per CTA, one item per CTA, every list in shared memory (s + 1 lists: 6 warps per SM for the 15-day window at K = 48).
+template <int NY, int K, int M, bool kPads>
+__global__ void __launch_bounds__(32)
+k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
+          const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
+          const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
+{
+    extern __shared__ __align__(16) float sm[];
+    const SlotsSmem<K> slots{sm + threadIdx.x};
+    net_item<NY, K, M, kPads>(blockIdx.x, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
+}
+
+// The same items on persistent CTAs of 4, 8 or 12 warps (one CTA per SM) that keep most suffix lists in TENSOR MEMORY: twice the
+// warps per SM, which is what the ALU pipe needs to stay busy through the networks' dependency chains.  Warps take items from a
+// global counter; warp w owns the TMEM lanes of quarter w % 4 and the column range (w / 4) * g.tm_cols.
+constexpr int kNetTmWarpsMax = 12;
+template <int NY, int K, int M, bool kPads>
+__global__ void __launch_bounds__(kNetTmWarpsMax * 32, 1)
+k_thr_net_tm(const float *__restrict__ x, int64_t C, uint32_t ld_t,
+             const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
+             const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand,
+             unsigned long long *__restrict__ next_item)
+{
+    extern __shared__ __align__(16) float sm[];
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {                                              // the whole tensor memory of this SM (the only CTA on it)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    SlotsMixed<K> slots;
+    slots.my = sm + (size_t)warp * g.tm_smem_slots * K * 32 + lane;
+    slots.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * g.tm_cols);
+    slots.n_tm = g.tm_lists;
+    slots.slot_f = g.M == 3 ? g.s : -1;
+    const unsigned long long n_items = (unsigned long long)(g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0));
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1ULL);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        net_item<NY, K, M, kPads>((int64_t)item, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // --------------------------------------------------------------------------------------------------------------------------
@@ -289,8 +416,22 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
     g.n_seq = n_doy + r;
     g.n_win = n_doy - r;                                                         // windows 0 .. n_doy-r-1 = sequence rows [k, k + W)
     g.n_steps = (g.n_win + g.s - 1) / g.s;
-    g.smem = (size_t)(g.M == 3 ? g.s + 1 : std::max(g.s, 1)) * g.K * 32 * sizeof(float);
+    const int n_slots = g.M == 3 ? g.s + 1 : std::max(g.s, 1);
+    const size_t list_bytes = (size_t)g.K * 32 * sizeof(float);
+    g.smem = n_slots * list_bytes;
     if (g.smem > 227 * 1024) return;
+    // tensor-memory variant: the largest CTA (12, 8 or 4 warps; warps of one lane quarter split the 512 columns) whose remaining
+    // shared-memory slots fit one SM - used when that is more warps per SM than the one-warp CTAs reach
+    g.tm_warps = 0;
+    const int warps_smem_only = (int)std::min<size_t>(32, (227 * 1024) / (g.smem + 1024));
+    for (int warps = kNetTmWarpsMax; warps >= 4; warps -= 4) {
+        const int cols = 512 / (warps / 4), lists = std::min(g.s - 1, cols / g.K);
+        const int smem_slots = n_slots - lists + (g.M == 1 ? 1 : 0);
+        if (lists < 1 || warps <= warps_smem_only) break;
+        if ((size_t)warps * smem_slots * list_bytes > 227 * 1024 - 256) continue;
+        g.tm_warps = warps; g.tm_lists = lists; g.tm_cols = cols; g.tm_smem_slots = smem_slots;
+        break;
+    }
 
     auto time_of = [&](int row, int y) -> int {
         if (y >= n_y) return -1;
@@ -328,9 +469,24 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
 
 template <int NY, int K, int M, bool kPads>
 static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out,
-                        const NetHandOver &hand, cudaStream_t st)
+                        const NetHandOver &hand, cudaStream_t st, bool allow_tmem)
 {
     const NetGeom &g = pl.geo;
+    if (allow_tmem && g.tm_warps > 0 && tb.next_item) {
+        const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
+        if (ld_t <= 0 || ld_t >= (1LL << 30)) return HDP_B200_ERR_UNSUPPORTED;
+        int dev = 0, sms = 0;
+        HDP_CUDA_TRY(cudaGetDevice(&dev));
+        HDP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t smem = (size_t)g.tm_warps * g.tm_smem_slots * g.K * 32 * sizeof(float);
+        HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net_tm<NY, K, M, kPads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HDP_CUDA_TRY(cudaMemsetAsync(tb.next_item, 0, sizeof(unsigned long long), st));
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, (items + g.tm_warps - 1) / g.tm_warps));
+        k_thr_net_tm<NY, K, M, kPads><<<grid, g.tm_warps * 32, smem, st>>>(x, C, (uint32_t)(ld_t * sizeof(float)), tb.seq_time, tb.win_day,
+                                                                          tb.irr_day, tb.irr_time, g, pl.sel, out, hand, tb.next_item);
+        HDP_LAUNCH_CHECK();
+        return HDP_B200_OK;
+    }
     HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net<NY, K, M, kPads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
     if (items > 0x7fffffffLL || ld_t <= 0 || ld_t >= (1LL << 30)) return HDP_B200_ERR_UNSUPPORTED;
@@ -340,13 +496,14 @@ static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, 
     return HDP_B200_OK;
 }
 
-int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st)
+int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st,
+               bool allow_tmem)
 {
     const NetGeom &g = pl.geo;
 #define HDP_NET_CASE(ny, k, m)                                                                             \
     if (g.NY == ny && g.K == k && g.M == m)                                                                \
-        return g.n_y == ny ? net_launch_t<ny, k, m, false>(pl, tb, x, C, ld_t, out, hand, st)              \
-                           : net_launch_t<ny, k, m, true>(pl, tb, x, C, ld_t, out, hand, st);
+        return g.n_y == ny ? net_launch_t<ny, k, m, false>(pl, tb, x, C, ld_t, out, hand, st, allow_tmem)  \
+                           : net_launch_t<ny, k, m, true>(pl, tb, x, C, ld_t, out, hand, st, allow_tmem);
     HDP_NET_INSTANCES(HDP_NET_CASE)
 #undef HDP_NET_CASE
     return HDP_B200_ERR_UNSUPPORTED;

@@ -29,7 +29,10 @@ struct NetGeom {
     int n_steps, steps_per_chunk, n_chunks;
     int n_irr;                          // days whose window is not a run of W consecutive rows (mirrored year end): row by row
     int64_t n_tiles;                    // 32-cell tiles
-    size_t smem;
+    size_t smem;                        // k_thr_net: bytes per one-warp CTA
+    // k_thr_net_tm (persistent CTAs, suffix lists in tensor memory): warps per CTA (0 = not used), suffix lists per warp kept in
+    // TMEM, TMEM columns per warp, shared-memory slots per warp
+    int tm_warps, tm_lists, tm_cols, tm_smem_slots;
 };
 
 struct NetPlan {
@@ -44,6 +47,7 @@ struct NetPlan {
 
 struct NetTables {                      // device copies (workspace)
     int *seq_time = nullptr, *win_day = nullptr, *irr_day = nullptr, *irr_time = nullptr;
+    unsigned long long *next_item = nullptr;   // k_thr_net_tm's work counter
 };
 
 // Decides whether the tables and quantiles fit k_thr_net and fills the plan (host only, no CUDA calls).
@@ -51,6 +55,7 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
               const int *pos_lo, const int *pos_hi, const int *mode_is_max, const int *mode_is_interp, const double *w_lo, const double *w_hi,
               int P, int64_t C, NetPlan &pl);
 void net_set_cells(NetPlan &pl, int64_t C);
-int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st);
+int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st,
+               bool allow_tmem);
 
 }  // namespace hdp

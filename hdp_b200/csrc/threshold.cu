@@ -1733,6 +1733,7 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.net.win_day = cv.take<int>((size_t)n_doy + W);
     L.net.irr_day = cv.take<int>((size_t)n_doy);
     L.net.irr_time = cv.take<int>((size_t)(n_doy / 4 + 1) * W * 32);      // at most a quarter of the days are irregular (net_plan)
+    L.net.next_item = cv.take<unsigned long long>(1);
     L.total = cv.off;
     return L;
 }
@@ -1742,6 +1743,7 @@ static std::atomic<int> g_force_ranked{0};
 static std::atomic<int> g_seg_light{1};          // test hook: 0 = the candidate path runs in k_thr_seg itself (no k_thr_cand)
 static std::atomic<int> g_seg_candidates{1};     // test hook: 0 = k_thr_seg orders every sample of a segment (no candidate filter)
 static std::atomic<int> g_net{1};                // test hook: 0 = no k_thr_net (the lane-per-cell network kernel, thr_net.cu)
+static std::atomic<int> g_net_tmem{1};           // test hook: 0 = k_thr_net keeps every list in shared memory (no k_thr_net_tm)
 
 // Everything that depends on the tables and quantiles only, built once per distinct (tables, quantiles) and shared by the
 // calls that use them (the lock covers the lookup, not the launches: calls on different devices / streams do not serialise).
@@ -1862,7 +1864,7 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
             const NetHandOver hand{L.handed_over, (int)blocks, geo.n_seg, geo.gc, geo.n_groups, kSegWarps};
             {
                 KernelTimer timer(kThrNet, st);
-                const int rc = net_launch(net, L.net, x, C, ld_t, d_out, hand, st);
+                const int rc = net_launch(net, L.net, x, C, ld_t, d_out, hand, st, g_net_tmem != 0);
                 if (rc != HDP_B200_OK) return rc;
             }
             KernelTimer timer(kThrSeg, st);
@@ -1936,6 +1938,7 @@ extern "C" {
 void hdp_b200_thresholds_force_generic(int on)
 {
     g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; g_seg_light = on != 4; g_net = on != 5;
+    g_net_tmem = on != 6;
 }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,

@@ -84,7 +84,8 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
  * variant k_thr_cand, with k_thr_seg behind it for the warps that one hands over - else k_thr_ranked, else
  * k_thr_generic); 1 = k_thr_generic for everything (gather + sort: any table, rows pooled any number of times);
  * 2 = k_thr_ranked instead of the segment kernels; 3 = k_thr_seg without the candidate filter; 4 = k_thr_seg with the
- * candidate filter but without k_thr_cand; 5 = the default without k_thr_net. */
+ * candidate filter but without k_thr_cand; 5 = the default without k_thr_net; 6 = the default with k_thr_net keeping every
+ * list in shared memory (no tensor-memory variant k_thr_net_tm). */
 void hdp_b200_thresholds_force_generic(int on);
 
 /* Host-buffer variant (chunked H2D / kernels / D2H pipeline, see csrc/host.cu).  d_keep: optional DEVICE buffer

@@ -215,8 +215,12 @@ def test_thresholds_network_kernel(core, calendar, years, radius, q, C):
     assert bits_equal(got, want)
     xt = dev(x.T.copy()).t()                                  # time-contiguous input: transposed on the device first
     assert bits_equal(core.thresholds_array(xt, wt, q).cpu().numpy(), want)
-    _lib.lib().hdp_b200_thresholds_force_generic(5)
     try:
+        _lib.lib().hdp_b200_thresholds_force_generic(6)      # every list in shared memory (no tensor-memory variant)
+        names = _net_launches(core, lambda: core.thresholds_array(dev(x), wt, q))
+        assert "k_thr_net" in names
+        assert bits_equal(core.thresholds_array(dev(x), wt, q).cpu().numpy(), want)
+        _lib.lib().hdp_b200_thresholds_force_generic(5)      # the segment kernels instead
         names = _net_launches(core, lambda: core.thresholds_array(dev(x), wt, q))
         assert "k_thr_net" not in names
         assert bits_equal(core.thresholds_array(dev(x), wt, q).cpu().numpy(), want)

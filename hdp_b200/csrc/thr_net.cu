@@ -79,18 +79,32 @@ __device__ __forceinline__ void net_issue_loads(float (&raw)[NY], const float *x
     }
 }
 
-// The requested ranks of a finished window: the list goes through a scratch slot (the positions are run-time values).
+// The requested ranks of a finished window: the list goes through a scratch slot (the positions are run-time values).  Five
+// percentiles at a time: their ten lookups are in flight together, then the f64 arithmetic, then the stores.
+__device__ __forceinline__ double net_value(float lower, float upper, int p, const NetSel &sel)
+{
+    // numba/np/arraymath.py:1697-1701 (separately rounded), :1669-1675 for q == 1
+    return sel.is_max[p] ? (double)upper : __dadd_rn(__dmul_rn((double)lower, sel.w_lo[p]), __dmul_rn((double)upper, sel.w_hi[p]));
+}
+
 template <int K>
-__device__ __forceinline__ void net_emit(const float (&list)[K], float *o, bool valid, double *dst, int P, const NetSel &sel)
+__device__ __forceinline__ void net_emit(const float (&list)[K], float *o, bool valid, double *__restrict__ dst, int P, const NetSel &sel)
 {
 #pragma unroll
     for (int e = 0; e < K; e++) o[e * 32] = list[e];
     if (!valid) return;
-    for (int p = 0; p < P; p++) {
-        const double lower = (double)o[sel.idx_lo[p] * 32], upper = (double)o[sel.idx_hi[p] * 32];
-        // numba/np/arraymath.py:1697-1701 (separately rounded), :1669-1675 for q == 1
-        dst[p] = sel.is_max[p] ? upper : __dadd_rn(__dmul_rn(lower, sel.w_lo[p]), __dmul_rn(upper, sel.w_hi[p]));
+    int p = 0;
+    for (; p + 5 <= P; p += 5) {
+        float lo[5], hi[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) { lo[j] = o[sel.idx_lo[p + j] * 32]; hi[j] = o[sel.idx_hi[p + j] * 32]; }
+        double v[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) v[j] = net_value(lo[j], hi[j], p + j, sel);
+#pragma unroll
+        for (int j = 0; j < 5; j++) dst[p + j] = v[j];
     }
+    for (; p < P; p++) dst[p] = net_value(o[sel.idx_lo[p] * 32], o[sel.idx_hi[p] * 32], p, sel);
 }
 
 // ---- where the lists that outlive a row step wait ----
@@ -250,10 +264,12 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
         if (n + 1 < n_rows) net_issue_loads<NY, kPads>(raw, xc, ld_t, t_next);       // row n + 1: in flight while this row is worked on
         if (n + 2 < n_rows) t_next = __ldg(row_table(n + 2, pb2, it2) + ty);         // its indices were fetched a row earlier
 
-        // ---- what this step does
+        // ---- what this step does (the day a finished window belongs to is fetched now and looked at after the networks)
         NetStepDesc d{it == 0 ? kStartEmpty : -1, -1, -1, -1, -1};
+        const int *emit_from = nullptr;
+        bool window_of_prefix = false;
         if (irregular) {
-            if (it == per - 1) d.emit_day = irr_day[pb];
+            if (it == per - 1) emit_from = irr_day + pb;
         } else if (pb < kPro) {
             if (it == s - 1) {
                 d.store_run = slot_f;
@@ -265,14 +281,15 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
                 const int i = s - 1 - it;                         //   behind it (M == 3) so that no extra merge is needed per window
                 if (M == 3 && it == 0) d.start = 0;
                 if (i > 0) d.store_run = i;
-                else d.emit_day = win_day[b * s];
+                else emit_from = win_day + b * s;
             } else if (it < s - 1) {                              // prefix lists of block b + M: window (b, it + 1)
-                d.emit_day = win_day[b * s + it + 1];
-                if (d.emit_day >= 0) d.other = it + 1;
+                emit_from = win_day + b * s + it + 1;
+                window_of_prefix = true;
             } else if (M == 3) {                                  // block b + 3 is complete: next pair of full blocks
                 d.other = slot_f; d.store_dst = 0; d.store_run = slot_f;
             }
         }
+        const int emit_day = emit_from ? __ldg(emit_from) : -1;
 
         // ---- order the row, merge it into the running list
         net::Sort<NY>::run(v);
@@ -285,6 +302,8 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
         }
 
         // ---- combine with a stored list; store; look up the requested ranks
+        d.emit_day = emit_day;
+        if (window_of_prefix && emit_day >= 0) d.other = it + 1;
         double *dst = out + ((size_t)(valid ? c : 0) * g.n_doy + max(d.emit_day, 0)) * g.P;
         if (d.other >= 0) {
             float tmp[K];

@@ -41,12 +41,14 @@ want = [("gpu__time_duration.sum", "duration"), ("smsp__inst_executed.sum", "war
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput %"),
         ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared wavefronts"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared bank conflicts"),
-        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %")]
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+        ("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "ALU pipe %"),
+        ("sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "FMA pipe %")]
 unit_scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 traffic = {}
 md = [f"# {tag}: `ncu --set full --clock-control none --import-source on`, first launch of each kernel, full cmip6_1deg grid (64 800 cells)\n",
-      "Reports: gpurun_out/prof_%s_{cand,hot,scan}.ncu-rep (not tracked); numbers copied from `ncu -i ... --page raw --csv`.\n" % tag]
-for short in ("cand", "seg", "hot", "scan"):
+      "Reports: gpurun_out/prof_%s_{net,hot,scan}.ncu-rep (not tracked); numbers copied from `ncu -i ... --page raw --csv`.\n" % tag]
+for short in ("net", "cand", "seg", "hot", "scan"):
     rep = os.path.join(out, f"prof_{tag}_{short}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -67,7 +69,12 @@ for short in ("cand", "seg", "hot", "scan"):
     stall = [(float(vals[i] or 0), n) for i, n in enumerate(hh) if n.startswith("smsp__average_warps_issue_stalled") and n.endswith("_per_issue_active.ratio")]
     top = sorted(stall, reverse=True)[:5]
     md.append("| top stalls (warps per issue-active cycle) | " + ", ".join(f"{n[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {v:.2f}" for v, n in top) + " |\n")
-    traffic[name.split("<")[0]] = {"dram_bytes_read": rd_b, "dram_bytes_write": wr_b, "dram_bytes": rd_b + wr_b, "cells": 64800, "capture": f"prof_{tag}_{short}.ncu-rep"}
+    key_name = name.split("<")[0].strip()
+    if key_name.startswith("hdp::"):
+        key_name = key_name[5:]
+    if key_name.startswith("k_thr_net"):           # k_thr_net_tm (tensor-memory variant) is timed under the same kernel id
+        key_name = "k_thr_net"
+    traffic[key_name] = {"dram_bytes_read": rd_b, "dram_bytes_write": wr_b, "dram_bytes": rd_b + wr_b, "cells": 64800, "capture": f"prof_{tag}_{short}.ncu-rep"}
 open(os.path.join(prof, f"{tag}_ncu_summary.md"), "w").write("".join(md))
 json.dump({"tag": tag, "kernels": traffic}, open(os.path.join(prof, "traffic.json"), "w"), indent=1)
 print("".join(md))

@@ -3,13 +3,13 @@
 #   plain_TAG.json          the bench line of the profiled command, run WITHOUT ncu first (must exit 0)
 #   launches_TAG.csv        ncu launch list (gpu__time_duration.sum per launch, --clock-control none) of the same command,
 #                           restricted to this library's kernels (the synthetic-input generation launches hundreds of torch kernels first)
-#   prof_TAG_{cand,hot,scan}.ncu-rep   one `--set full` capture of the first launch of each kernel (full 64 800-cell grid)
+#   prof_TAG_{net,hot,scan}.ncu-rep   one `--set full` capture of the first launch of each kernel (full 64 800-cell grid)
 # Numbers printed under ncu are never bench values.
 TAG=$1
 CMD="python bench.py --no-e2e --no-cpu --steps 1 --warmup 1"
 $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_|hdp" -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
-for k in cand:k_thr_cand hot:k_hot_words scan:k_scan; do
+for k in net:k_thr_net hot:k_hot_words scan:k_scan; do
   short=${k%%:*}; name=${k##*:}
   ncu --set full --clock-control none --import-source on -k regex:"$name" -c 1 -f -o gpurun_out/prof_${TAG}_$short $CMD > gpurun_out/ncu_${TAG}_$short.log 2>&1
 done

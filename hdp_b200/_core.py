@@ -76,9 +76,22 @@ def _strides(x):
     return int(ld_t), int(ld_c)
 
 
-def thresholds_array(temps, tables: WindowTables, percentiles: Sequence[float], out=None):
-    """``temps`` f32 ``[T_b, C]`` -> thresholds f64 ``[C, n_doy, P]`` (reference dims (<cells>, doy, percentile))."""
+def _unit_code(units) -> int:
+    """``units`` of the samples handed to the kernels: they are converted to Celsius as they are loaded (the unit step of
+    format_standard_measures, reference hdp/measure.py:136-149, fused into the load stage)."""
+    if units is None:
+        return 0
+    try:
+        return TEMPERATURE_UNIT_CODES[units]
+    except KeyError:
+        raise ValueError(f"units must be one of {sorted(TEMPERATURE_UNIT_CODES)}") from None
+
+
+def thresholds_array(temps, tables: WindowTables, percentiles: Sequence[float], out=None, units=None):
+    """``temps`` f32 ``[T_b, C]`` -> thresholds f64 ``[C, n_doy, P]`` (reference dims (<cells>, doy, percentile)).
+    ``units``: 'degC' (default), 'degK' or 'degF' samples - see :func:`_unit_code`."""
     torch = _torch()
+    unit = _unit_code(units)
     _check_measure(temps, "temps")
     L = _lib.lib()
     T_b, C = temps.shape
@@ -91,10 +104,10 @@ def thresholds_array(temps, tables: WindowTables, percentiles: Sequence[float], 
     elif not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and tuple(out.shape) == (C, n_doy, P)):
         raise TypeError("out must be a contiguous float64 CUDA tensor [C, n_doy, P]")
     with torch.cuda.device(temps.device):
-        nbytes = L.hdp_b200_thresholds_workspace_bytes(C, T_b, ld_t, ld_c, n_doy, n_y, W, P)
+        nbytes = L.hdp_b200_thresholds_workspace_bytes(C, T_b, ld_t, ld_c, n_doy, n_y, W, P, unit)
         ws = _workspace(temps.device, nbytes)
         rc = L.hdp_b200_thresholds(temps.data_ptr(), C, T_b, ld_t, ld_c, _hp(ti), _hp(wr), n_doy, n_y, W, _hp(q), P,
-                                   out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                   out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, unit)
     _lib.check(rc, "hdp_b200_thresholds")
     return out
 
@@ -115,10 +128,12 @@ def _check_thr(thr, C):
         raise TypeError("thresholds must be a contiguous float64 CUDA tensor [C, n_doy, P]")
 
 
-def metrics_array(measure, thresholds, doy_map, defs, season_north, season_south, is_south=None, out=None):
+def metrics_array(measure, thresholds, doy_map, defs, season_north, season_south, is_south=None, out=None, units=None):
     """``measure`` f32 ``[T, C]``, ``thresholds`` f64 ``[C, n_doy, P]`` -> uint16 ``[4, P, D, Y, C]``
-    (planes HWF, HWN, HWD, HWA; the reference's int64 ``[P, D, C, 4, Y]`` is ``out.permute(1, 2, 4, 0, 3)`` widened)."""
+    (planes HWF, HWN, HWD, HWA; the reference's int64 ``[P, D, C, 4, Y]`` is ``out.permute(1, 2, 4, 0, 3)`` widened).
+    ``units`` of the measure's samples as for :func:`thresholds_array`."""
     torch = _torch()
+    unit = _unit_code(units)
     _check_measure(measure, "measure")
     T, C = measure.shape
     _check_thr(thresholds, C)
@@ -145,7 +160,7 @@ def metrics_array(measure, thresholds, doy_map, defs, season_north, season_south
         rc = L.hdp_b200_metrics(measure.data_ptr(), C, T, ld_t, ld_c, thresholds.data_ptr(), n_doy, P, _hp(dm),
                                 _hp(df), D, _hp(sn), _hp(ss), Y,
                                 south_t.data_ptr() if south_t is not None else None,
-                                out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, unit)
     _lib.check(rc, "hdp_b200_metrics")
     return out
 
@@ -282,7 +297,7 @@ def release_resident() -> None:
 
 
 def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequence[float], out: Optional[np.ndarray] = None,
-                    keep=None) -> np.ndarray:
+                    keep=None, units=None) -> np.ndarray:
     """Host arrays in, host array out (chunked copy/compute pipeline inside the library).  ``keep``: a float64 CUDA tensor
     ``[C, n_doy, P]`` that also receives the thresholds, or True to let the library allocate one and remember it for the
     metric pass (the returned array is then read-only, see :func:`resident_thresholds`)."""
@@ -302,7 +317,8 @@ def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequen
         out = np.empty((C, tables.n_doy, q.size), np.float64)
     assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (C, tables.n_doy, q.size)
     rc = L.hdp_b200_thresholds_host(_hp(temps), C, T_b, ld_t, ld_c, _hp(ti), _hp(wr), tables.n_doy, tables.n_y,
-                                    tables.width, _hp(q), int(q.size), _hp(out), keep.data_ptr() if keep is not None else None)
+                                    tables.width, _hp(q), int(q.size), _hp(out), keep.data_ptr() if keep is not None else None,
+                                    _unit_code(units))
     _lib.check(rc, "hdp_b200_thresholds_host")
     if remember:
         out.flags.writeable = False
@@ -311,7 +327,7 @@ def thresholds_host(temps: np.ndarray, tables: WindowTables, percentiles: Sequen
 
 
 def metrics_host(measure: np.ndarray, thresholds, doy_map, defs, season_north, season_south,
-                 is_south=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+                 is_south=None, out: Optional[np.ndarray] = None, units=None) -> np.ndarray:
     """``thresholds``: float64 ``[C, n_doy, P]`` as a host array, or as a CUDA tensor (device-resident: no upload).  A host
     array that :func:`thresholds_host` returned with ``keep=True`` is recognised and its device copy used."""
     torch = _torch()
@@ -339,7 +355,7 @@ def metrics_host(measure: np.ndarray, thresholds, doy_map, defs, season_north, s
     assert out.flags.c_contiguous and out.dtype == np.uint16 and out.shape == (4, P, D, Y, C)
     rc = L.hdp_b200_metrics_host(_hp(measure), C, T, ld_t, ld_c, _hp(thr) if thr is not None else None,
                                  d_thr.data_ptr() if d_thr is not None else None, n_doy, P, _hp(dm), _hp(df), D, _hp(sn), _hp(ss), Y,
-                                 _hp(south) if south is not None else None, _hp(out))
+                                 _hp(south) if south is not None else None, _hp(out), _unit_code(units))
     _lib.check(rc, "hdp_b200_metrics_host")
     return out
 

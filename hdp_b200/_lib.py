@@ -22,13 +22,13 @@ SIGNATURES = {
     "hdp_b200_strerror": (ctypes.c_char_p, [_int]),
     "hdp_b200_device_info": (_int, [_p, _p, _p]),
     "hdp_b200_launch_count": (_i64, []),
-    "hdp_b200_thresholds_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _int, _int, _int]),
-    "hdp_b200_thresholds": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p, _sz, _p]),
+    "hdp_b200_thresholds_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _int, _int, _int, _int]),
+    "hdp_b200_thresholds": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p, _sz, _p, _int]),
     "hdp_b200_thresholds_force_generic": (None, [_int]),
-    "hdp_b200_thresholds_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p]),
+    "hdp_b200_thresholds_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p, _int]),
     "hdp_b200_metrics_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _int, _int, _int, _p]),
-    "hdp_b200_metrics": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p, _p, _sz, _p]),
-    "hdp_b200_metrics_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p]),
+    "hdp_b200_metrics": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p, _p, _sz, _p, _int]),
+    "hdp_b200_metrics_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p, _int]),
     "hdp_b200_host_release": (None, []),
     "hdp_b200_metrics_run_filter": (None, [_int]),
     "hdp_b200_heat_index": (_int, [_p, _p, _i64, _p, _p]),
@@ -65,7 +65,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)          # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
-        if L.hdp_b200_abi_version() != 2:
+        if L.hdp_b200_abi_version() != 3:
             raise RuntimeError("libhdp_b200.so ABI version mismatch; rebuild with `python -m hdp_b200.build --force`")
         _LIB = L
     return _LIB

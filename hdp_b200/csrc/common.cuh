@@ -75,6 +75,20 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) { uint32_t
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
 #endif
 
+#ifdef __CUDACC__
+// hdp.measure's unit conversions (reference hdp/measure.py:10-41) as the kernels apply them to every sample they load
+// (`input_unit` of the C ABI): 0 = already Celsius, 1 = Kelvin (temp -= 273.15), 2 = Fahrenheit ((temp - 32) / 1.8); float32
+// arithmetic with separately rounded operations, bit-identical to the reference's NumPy float32 array arithmetic.
+__device__ __forceinline__ float to_celsius_f(float v, int unit)
+{
+    if (unit == 1) return __fsub_rn(v, 273.15f);
+    if (unit == 2) return __fdiv_rn(__fsub_rn(v, 32.0f), 1.8f);
+    return v;
+}
+#endif
+// Dense [n] float32 -> Celsius, out of place or in place (measure.cu).
+int to_celsius_launch(const float *src, int64_t n, int unit, float *dst, cudaStream_t st);
+
 // Copies the strided measure array into a time-major, cell-contiguous [T, C] buffer.
 int normalize_layout(const float *src, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c, float *dst, cudaStream_t st);
 

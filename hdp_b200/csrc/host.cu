@@ -35,13 +35,13 @@ namespace hdp {
 int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                       const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                       const double *h_q, int P, double *d_out,
-                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident);
+                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident, int input_unit);
 int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                    const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
                    const int32_t *h_defs, int D,
                    const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                    const uint8_t *d_is_south, uint16_t *d_out,
-                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident);
+                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident, int input_unit);
 
 constexpr int kSlots = 3;
 constexpr int kMaxDevices = 64;
@@ -343,7 +343,7 @@ void hdp_b200_host_release(void)
 
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
-                             const double *h_q, int P, double *h_out, double *d_keep)
+                             const double *h_q, int P, double *h_out, double *d_keep, int input_unit)
 {
     if (C < 0 || T_b <= 0 || n_doy <= 0 || n_y <= 0 || W <= 0 || P <= 0) return HDP_B200_ERR_INVALID;
     if (C == 0) return HDP_B200_OK;
@@ -359,7 +359,7 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
     const size_t out_per_cell = (size_t)n_doy * P * sizeof(double);
     const int64_t chunk = pick_chunk(C, (size_t)T_b * sizeof(float), (size_t)64 << 20);
     const int64_t dl_t = ld_c == 1 ? chunk : 1, dl_c = ld_c == 1 ? 1 : T_b;
-    const size_t ws_bytes = hdp_b200_thresholds_workspace_bytes(chunk, T_b, dl_t, dl_c, n_doy, n_y, W, P);
+    const size_t ws_bytes = hdp_b200_thresholds_workspace_bytes(chunk, T_b, dl_t, dl_c, n_doy, n_y, W, P, input_unit);
     if ((rc = ctx->ws.reserve(ws_bytes))) return rc;
     for (int i = 0; i < kSlots; i++) {
         if ((rc = ctx->x[i].reserve((size_t)chunk * T_b * sizeof(float)))) return rc;
@@ -382,7 +382,7 @@ int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->in_ready[slot], 0));
         if (!d_keep) HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_k, ctx->out_done[slot], 0));
         HDP_HOST_TRY(thresholds_launch((const float *)ctx->x[slot].p, nc, T_b, a, b, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P,
-                                       d_chunk_out, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
+                                       d_chunk_out, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0, input_unit));
         HDP_HOST_CUDA(cudaEventRecord(ctx->k_done[slot], ctx->s_k));
         // stage 3: results
         HDP_HOST_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->k_done[slot], 0));
@@ -397,7 +397,7 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
                           const double *h_thr, const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
                           const int32_t *h_defs, int D,
                           const int32_t *h_season_north, const int32_t *h_season_south, int Y,
-                          const uint8_t *h_is_south, uint16_t *h_out)
+                          const uint8_t *h_is_south, uint16_t *h_out, int input_unit)
 {
     if (C < 0 || T <= 0 || n_doy <= 0 || P <= 0 || D <= 0 || Y < 0 || !h_doy_map) return HDP_B200_ERR_INVALID;
     if (C == 0 || Y == 0) return HDP_B200_OK;
@@ -444,7 +444,7 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
                                     d_thr ? d_thr + (size_t)c0 * n_doy * P : (const double *)ctx->aux[slot].p, n_doy, P, h_doy_map,
                                     h_defs, D, h_season_north, h_season_south, Y,
                                     h_is_south ? (const uint8_t *)ctx->south[slot].p : nullptr,
-                                    (uint16_t *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0));
+                                    (uint16_t *)ctx->out[slot].p, ctx->ws.p, ws_bytes, ctx->s_k, chunk, i > 0, input_unit));
         HDP_HOST_CUDA(cudaEventRecord(ctx->k_done[slot], ctx->s_k));
 
         // device chunk is [rows, nc]; host array is [rows, C]

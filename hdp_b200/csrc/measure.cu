@@ -42,14 +42,6 @@ __device__ __forceinline__ float heat_index_f(float temp, float rel_humid)
     return __double2float_rn(hi);
 }
 
-// unit: 0 = already Celsius, 1 = Kelvin (temp -= 273.15), 2 = Fahrenheit ((temp - 32) / 1.8): float32 arithmetic
-__device__ __forceinline__ float to_celsius_f(float v, int unit)
-{
-    if (unit == 1) return __fsub_rn(v, 273.15f);
-    if (unit == 2) return __fdiv_rn(__fsub_rn(v, 32.0f), 1.8f);
-    return v;
-}
-
 // mode 0: out = heat_index(temp [F], rh [%])                                              (the reference's ufunc)
 // mode 1: out = F->C(heat_index(C->F(temp [C]), rh [%] or rh [g/g] * 100))                 (format_standard_measures' branch)
 // mode 2: out = to_celsius(temp, unit)                                                     (convert_temp_units)
@@ -99,6 +91,12 @@ static int launch_measure(const float *temp, const float *rh, int64_t n, int fla
     k_measure<kMode><<<(unsigned)blocks, 256, 0, st>>>(temp, rh, n, flag, out);
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;
+}
+
+int to_celsius_launch(const float *src, int64_t n, int unit, float *dst, cudaStream_t st)
+{
+    if (unit < 0 || unit > 2) return HDP_B200_ERR_INVALID;
+    return launch_measure<2>(src, nullptr, n, unit, dst, st);
 }
 
 }  // namespace hdp

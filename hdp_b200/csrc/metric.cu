@@ -43,7 +43,7 @@ __device__ __forceinline__ void or_if_gt(uint32_t &m, float v, float t, uint32_t
     asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(v), "f"(t), "r"(bit));
 }
 
-template <int PG, int J0>
+template <int PG, int J0, int UNIT>
 __device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const float *const (&xp)[kHotYears], const int (&jo)[kHotYears],
                                          const int (&nb)[kHotYears], int64_t ld_t, const float *ts)
 {
@@ -53,6 +53,12 @@ __device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const flo
 #pragma unroll
         for (int j = 0; j < kHotDays; j++)                 // NaN = never hot: days outside the word
             v[y][j] = (unsigned)(J0 + j - jo[y]) < (unsigned)nb[y] ? __ldg(xp[y] + (int64_t)(J0 + j) * ld_t) : __int_as_float(0x7fc00000);
+    if (UNIT != 0) {                                       // Kelvin / Fahrenheit input, converted as it is loaded (NaN stays NaN)
+#pragma unroll
+        for (int y = 0; y < kHotYears; y++)
+#pragma unroll
+            for (int j = 0; j < kHotDays; j++) v[y][j] = to_celsius_f(v[y][j], UNIT);
+    }
 #pragma unroll
     for (int j = 0; j < kHotDays; j++) {
         float t[PG];
@@ -65,7 +71,7 @@ __device__ __forceinline__ void hot_half(uint32_t (&m)[kHotYears][PG], const flo
     }
 }
 
-template <int PG>
+template <int PG, int UNIT>
 __global__ void __launch_bounds__(256, PG <= 10 ? 3 : 2)
 k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
             const double *__restrict__ thr, int n_doy, int P,
@@ -135,8 +141,8 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
 #pragma unroll
                 for (int q = 0; q < PG; q++) m[y][q] = 0u;
             const float *ts = thr_s + (size_t)(pg / PG) * (kTileDoy * PG * kTilePad) + lane;
-            hot_half<PG, 0>(m, xp, jo, nb, ld_t, ts);
-            if (j_hi > kHotDays) hot_half<PG, kHotDays>(m, xp, jo, nb, ld_t, ts);      // warp-uniform
+            hot_half<PG, 0, UNIT>(m, xp, jo, nb, ld_t, ts);
+            if (j_hi > kHotDays) hot_half<PG, kHotDays, UNIT>(m, xp, jo, nb, ld_t, ts);      // warp-uniform
 #pragma unroll
             for (int y = 0; y < kHotYears; y++)
 #pragma unroll
@@ -577,8 +583,9 @@ static bool bad_dims(int64_t C, int64_t T, int n_doy, int P)
 static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, int64_t ld_c,
                          const double *d_thr, int n_doy, int P, const int32_t *h_doy_map,
                          int Y, void *ws, size_t ws_bytes, cudaStream_t st, WordPlan &plan, Layout &L,
-                         int64_t carve_cells = 0, bool tables_resident = false)
+                         int64_t carve_cells = 0, bool tables_resident = false, int input_unit = 0)
 {
+    if (input_unit < 0 || input_unit > 2) return HDP_B200_ERR_INVALID;
     int rc = build_words(h_doy_map, T, n_doy, plan);
     if (rc != HDP_B200_OK) return rc;
     const int K = (int)plan.words.size();
@@ -602,10 +609,16 @@ static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t l
     const size_t smem = (size_t)kTileDoy * Ppad * kTilePad * sizeof(float);
     dim3 grid((unsigned)((C + kTileCells - 1) / kTileCells), (unsigned)plan.n_blk);
     KernelTimer timer(kHotWords, st);
+#define HDP_LAUNCH_HOT_U(PG, U)                                                                                    \
+    do {                                                                                                           \
+        HDP_CUDA_TRY(cudaFuncSetAttribute(k_hot_words<PG, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_hot_words<PG, U><<<grid, 256, smem, st>>>(x, C, ld_t, d_thr, n_doy, P, L.words, L.blk_start, L.blk_words, K, L.hot); \
+    } while (0)
 #define HDP_LAUNCH_HOT(PG)                                                                                         \
     do {                                                                                                           \
-        HDP_CUDA_TRY(cudaFuncSetAttribute(k_hot_words<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_hot_words<PG><<<grid, 256, smem, st>>>(x, C, ld_t, d_thr, n_doy, P, L.words, L.blk_start, L.blk_words, K, L.hot); \
+        if (input_unit == 0) HDP_LAUNCH_HOT_U(PG, 0);                                                              \
+        else if (input_unit == 1) HDP_LAUNCH_HOT_U(PG, 1);                                                         \
+        else HDP_LAUNCH_HOT_U(PG, 2);                                                                              \
     } while (0)
     switch (pg) {
     case 4: HDP_LAUNCH_HOT(4); break;
@@ -615,6 +628,7 @@ static int run_hot_words(const float *d_measure, int64_t C, int64_t T, int64_t l
     default: HDP_LAUNCH_HOT(20); break;
     }
 #undef HDP_LAUNCH_HOT
+#undef HDP_LAUNCH_HOT_U
     HDP_LAUNCH_CHECK();
     return HDP_B200_OK;
 }
@@ -636,7 +650,7 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
                    const int32_t *h_defs, int D,
                    const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                    const uint8_t *d_is_south, uint16_t *d_out,
-                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident)
+                   void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident, int input_unit)
 {
     if (bad_dims(C, T, n_doy, P) || D <= 0 || Y < 0) return HDP_B200_ERR_INVALID;
     if ((T > 0 && !h_doy_map) || !h_defs || (Y > 0 && (!h_season_north || !h_season_south))) return HDP_B200_ERR_INVALID;
@@ -670,7 +684,7 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
     WordPlan plan;
     Layout L;
     int rc = run_hot_words(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, Y, d_workspace, workspace_bytes, st, plan, L,
-                            carve_cells, tables_resident);
+                            carve_cells, tables_resident, input_unit);
     if (rc != HDP_B200_OK || C == 0 || Y == 0) return rc;
     const int K = (int)plan.words.size();
 
@@ -820,10 +834,10 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
                      const int32_t *h_defs, int D,
                      const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                      const uint8_t *d_is_south, uint16_t *d_out,
-                     void *d_workspace, size_t workspace_bytes, void *stream)
+                     void *d_workspace, size_t workspace_bytes, void *stream, int input_unit)
 {
     return metrics_launch(d_measure, C, T, ld_t, ld_c, d_thr, n_doy, P, h_doy_map, h_defs, D, h_season_north, h_season_south, Y,
-                          d_is_south, d_out, d_workspace, workspace_bytes, stream, C, false);
+                          d_is_south, d_out, d_workspace, workspace_bytes, stream, C, false, input_unit);
 }
 
 }  // extern "C"

@@ -256,11 +256,15 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
 
     for (int n = 0; n < n_rows; n++) {
         float v[NY];
+        if (g.unit == 0) {                                        // (warp-uniform; one branch per row, not per sample)
 #pragma unroll
-        for (int y = 0; y < NY; y++) {
-            v[y] = raw[y];
-            bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);             // non-finite census on the otherwise idle FMA pipe: NaN or +-inf -> NaN
+            for (int y = 0; y < NY; y++) v[y] = raw[y];
+        } else {                                                  // Kelvin input: converted as it arrives, one FADD per sample (pads stay
+#pragma unroll                                                    // the most negative values); Fahrenheit input is converted beforehand
+            for (int y = 0; y < NY; y++) v[y] = to_celsius_f(raw[y], 1);
         }
+#pragma unroll
+        for (int y = 0; y < NY; y++) bad_acc = __fmaf_rn(v[y], 0.0f, bad_acc);   // non-finite census on the otherwise idle FMA pipe
         if (n + 1 < n_rows) net_issue_loads<NY, kPads>(raw, xc, ld_t, t_next);       // row n + 1: in flight while this row is worked on
         if (n + 2 < n_rows) t_next = __ldg(row_table(n + 2, pb2, it2) + ty);         // its indices were fetched a row earlier
 

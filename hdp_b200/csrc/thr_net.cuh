@@ -24,6 +24,7 @@ struct NetGeom {
     int NY, K, M;                       // template instance: samples per row (padded), list length, blocks per window (1 or 3)
     int s;                              // rows per block: W == M * s
     int W, n_y, n_doy, P;
+    int unit;                           // input unit of the samples (common.cuh to_celsius_f), converted as they are loaded
     int n_seq;                          // rows of the linear row sequence (n_doy + r); row n_seq of seq_time is the all-pad row
     int n_win;                          // windows 0 .. n_win-1 of W consecutive sequence rows; window k belongs to day win_day[k] (or -1)
     int n_steps, steps_per_chunk, n_chunks;

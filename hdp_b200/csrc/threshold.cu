@@ -448,6 +448,7 @@ struct SegGeom {
     int ny_magic;                       // (k * ny_magic) >> 16 == k / n_y for k < 1024
     int n_y;                            // samples per day-of-year row
     int cand_m;                         // candidate filter: keep the samples >= min over rows of the row's cand_m-th largest; 0 = off
+    int unit;                           // k_thr_seg behind k_thr_net only: input unit of the samples (to_celsius_f), else 0
 };
 
 struct SelShared {                      // SelTable without the k_thr_ranked bookkeeping, in shared memory
@@ -682,6 +683,8 @@ k_thr_seg(const float *__restrict__ temps, int64_t C, int64_t ld_t,
         for (int k = tid / kSegWarps; k < NE; k += 32)            // asynchronous 4-byte copies: every load of the tile is in flight at once
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_dst + 4u * k), "l"(src + (int64_t)st[k] * ld_t) : "memory");
         asm volatile("cp.async.wait_all;" ::: "memory");
+        if (geo.unit != 0)                                        // Kelvin / Fahrenheit input: every thread converts what it gathered
+            for (int k = tid / kSegWarps; k < NE; k += 32) dst[k] = to_celsius_f(dst[k], geo.unit);
     }
     __syncthreads();                                              // the tile is complete
     [&]() {                                                       // everything below is warp-private: `return` leaves this warp's item
@@ -1681,6 +1684,7 @@ static void plan_seg(const int32_t *time_index, const int32_t *win_rows, int64_t
         sp.geo.ny_magic = magic;
         sp.geo.n_y = n_y;
         sp.geo.cand_m = 0;
+        sp.geo.unit = 0;
         sp.usable = true;
         return;
     }
@@ -1712,11 +1716,11 @@ struct ThrLayout {
     NetTables net;                                   // k_thr_net tables
 };
 
-static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_norm, int n_doy, int n_y, int W)
+static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bool need_copy, int n_doy, int n_y, int W)
 {
     ThrLayout L;
     Carver cv(ws, ws_bytes);
-    if (need_norm) L.xn = cv.take<float>((size_t)C * T_b);
+    if (need_copy) L.xn = cv.take<float>((size_t)C * T_b);      // transposed and / or converted copy of the samples
     L.time_index = cv.take<int>((size_t)n_doy * n_y);
     L.win_rows = cv.take<int>((size_t)n_doy * W);
     L.op_off = cv.take<int>((size_t)n_doy + 1);
@@ -1763,9 +1767,10 @@ struct ThrPlans {
 int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                       const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                       const double *h_q, int P, double *d_out,
-                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident)
+                      void *d_workspace, size_t workspace_bytes, void *stream, int64_t carve_cells, bool tables_resident, int input_unit)
 {
     if (bad_dims(C, T_b, n_doy, n_y, W, P) || !h_time_index || !h_win_rows || !h_q) return HDP_B200_ERR_INVALID;
+    if (input_unit < 0 || input_unit > 2) return HDP_B200_ERR_INVALID;
     if (C > 0 && (!d_temps || !d_out)) return HDP_B200_ERR_INVALID;
     if (C > 0 && T_b == 0) return HDP_B200_ERR_INVALID;                      // nothing to index into
     if (P > HDP_B200_MAX_PERCENTILES) return HDP_B200_ERR_UNSUPPORTED;
@@ -1784,7 +1789,7 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
 
     cudaStream_t st = (cudaStream_t)stream;
     const bool need_norm = ld_c != 1;
-    ThrLayout L = carve_thr(d_workspace, workspace_bytes, std::max(C, carve_cells), T_b, need_norm, n_doy, n_y, W);
+    ThrLayout L = carve_thr(d_workspace, workspace_bytes, std::max(C, carve_cells), T_b, need_norm || input_unit != 0, n_doy, n_y, W);
     if (!d_workspace || L.total > workspace_bytes) return HDP_B200_ERR_WORKSPACE;
     const float *x = d_temps;
     if (need_norm) {
@@ -1793,6 +1798,21 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         x = L.xn;
         ld_t = C;
     }
+    // Kelvin / Fahrenheit input: k_thr_net converts every sample as it loads it (nothing extra moves); the other kernels work
+    // on a converted copy.  `convert_copy` is called on the paths that need it.
+    auto convert_copy = [&]() -> int {
+        if (input_unit == 0) return HDP_B200_OK;
+        if (x != L.xn && ld_t != C) {                                        // rows with a pitch: densify first
+            int rc = normalize_layout(x, C, T_b, ld_t, 1, L.xn, st);
+            if (rc != HDP_B200_OK) return rc;
+            x = L.xn;
+            ld_t = C;
+        }
+        int rc = to_celsius_launch(x, C * T_b, input_unit, L.xn, st);
+        x = L.xn;
+        input_unit = 0;
+        return rc;
+    };
     if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
 
     std::shared_ptr<ThrPlans> plans;
@@ -1847,11 +1867,13 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         const int64_t n_chunks = (geo.n_groups + geo.gc - 1) / geo.gc;
         const int64_t blocks = n_chunks * geo.n_seg * geo.gc;
         if (blocks > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
+        if (input_unit == 2) { const int rc = convert_copy(); if (rc != HDP_B200_OK) return rc; }   // (the division stays out of k_thr_net)
         if (plans->net.usable && g_net && g_seg_light && g_seg_candidates && (size_t)blocks <= L.handed_over_count) {
             // high quantiles, regular windows: the lane-per-cell network kernel; cells with NaN / +-inf samples put all their
             // segments on k_thr_seg's hand-over list, which runs behind it (8 us when the list is empty)
             NetPlan net = plans->net;                                           // (tables are shared; the cell split is per call)
             net_set_cells(net, C);
+            net.geo.unit = input_unit;
             if (!tables_resident) {
                 HDP_CUDA_TRY(cudaMemcpyAsync(L.net.seq_time, net.seq_time.data(), sizeof(int) * net.seq_time.size(), cudaMemcpyHostToDevice, st));
                 HDP_CUDA_TRY(cudaMemcpyAsync(L.net.win_day, net.win_day.data(), sizeof(int) * net.win_day.size(), cudaMemcpyHostToDevice, st));
@@ -1869,11 +1891,13 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
             }
             KernelTimer timer(kThrSeg, st);
             const unsigned turns = (unsigned)std::min<int64_t>(blocks, 2 * 148 * 4);
+            geo.unit = input_unit;                                              // the handed-over cells are converted as they are gathered
             k_thr_seg<<<turns, kSegWarps * 32, smem, st>>>(x, C, ld_t, L.seg_time, L.seg_ne, (const uint4 *)L.doy_rng, geo, sel, P,
                                                            (int)b, n_doy, d_out, L.handed_over, (int)blocks);
             HDP_LAUNCH_CHECK();
             return HDP_B200_OK;
         }
+        { const int rc = convert_copy(); if (rc != HDP_B200_OK) return rc; }
         if (geo.cand_m > 0 && g_seg_light && (size_t)blocks <= L.handed_over_count) {
             // high quantiles: the light kernel first, then k_thr_seg for the warps it handed over (non-finite samples,
             // more than kLCap candidates), a small grid taking the blocks on the hand-over list in turns
@@ -1899,6 +1923,7 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
         HDP_LAUNCH_CHECK();
         return HDP_B200_OK;
     }
+    { const int rc = convert_copy(); if (rc != HDP_B200_OK) return rc; }
     if (plan.usable && !g_force_generic) {
         if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.op_off, plan.op_off.data(), sizeof(int) * plan.op_off.size(), cudaMemcpyHostToDevice, st));
         if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.ops, plan.ops.data(), sizeof(int) * plan.ops.size(), cudaMemcpyHostToDevice, st));
@@ -1942,20 +1967,20 @@ void hdp_b200_thresholds_force_generic(int on)
 }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
-                                           int n_doy, int n_y, int W, int P)
+                                           int n_doy, int n_y, int W, int P, int input_unit)
 {
     (void)ld_t;
     if (bad_dims(C, T_b, n_doy, n_y, W, P)) return 0;
-    return carve_thr(nullptr, 0, C, T_b, ld_c != 1, n_doy, n_y, W).total;
+    return carve_thr(nullptr, 0, C, T_b, ld_c != 1 || input_unit != 0, n_doy, n_y, W).total;
 }
 
 int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                         const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                         const double *h_q, int P, double *d_out,
-                        void *d_workspace, size_t workspace_bytes, void *stream)
+                        void *d_workspace, size_t workspace_bytes, void *stream, int input_unit)
 {
     return thresholds_launch(d_temps, C, T_b, ld_t, ld_c, h_time_index, h_win_rows, n_doy, n_y, W, h_q, P, d_out,
-                             d_workspace, workspace_bytes, stream, C, false);
+                             d_workspace, workspace_bytes, stream, C, false, input_unit);
 }
 
 }  // extern "C"

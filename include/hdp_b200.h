@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define HDP_B200_ABI_VERSION 2
+#define HDP_B200_ABI_VERSION 3
 
 #define HDP_B200_OK                 0
 #define HDP_B200_ERR_INVALID       (-1)  /* null pointer, negative size, quantile outside [0,1] or NaN, bad table entry */
@@ -68,15 +68,23 @@ int         hdp_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
  *                 window_samples[d] == time_index[win_rows[d]].ravel() is the reference's table
  *   h_q           f64 [P]           quantiles in [0, 1]
  *   d_out         f64 [C, n_doy, P] (the reference's (<cells>, doy, percentile) order)
+ *   input_unit    unit of the samples, converted to Celsius AS THEY ARE LOADED with the reference's float32 arithmetic
+ *                 (hdp/measure.py:10-41): 0 = Celsius (no conversion), 1 = Kelvin (x - 273.15), 2 = Fahrenheit ((x - 32) / 1.8).
+ *                 Raw model output then needs no converted copy: format_standard_measures' unit step is fused into the load
+ *                 stage of the kernels on the hot path (k_thr_net, k_hot_words; other threshold kernels convert a copy first).
  * ------------------------------------------------------------------------------------------------- */
+#define HDP_B200_UNIT_CELSIUS    0
+#define HDP_B200_UNIT_KELVIN     1
+#define HDP_B200_UNIT_FAHRENHEIT 2
+
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
-                                           int n_doy, int n_y, int W, int P);
+                                           int n_doy, int n_y, int W, int P, int input_unit);
 
 int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                         const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                         const double *h_q, int P,
                         double *d_out,
-                        void *d_workspace, size_t workspace_bytes, void *stream);
+                        void *d_workspace, size_t workspace_bytes, void *stream, int input_unit);
 
 /* Test hook: which kernel hdp_b200_thresholds uses.  0 = default (k_thr_net, the lane-per-cell network kernel, where the
  * tables and quantiles allow - high quantiles, windows of consecutive rows, at most 32 samples per row - with k_thr_seg
@@ -95,7 +103,7 @@ void hdp_b200_thresholds_force_generic(int on);
 int hdp_b200_thresholds_host(const float *h_temps, int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,
                              const int32_t *h_time_index, const int32_t *h_win_rows, int n_doy, int n_y, int W,
                              const double *h_q, int P,
-                             double *h_out, double *d_keep);
+                             double *h_out, double *d_keep, int input_unit);
 
 /* ---------------------------------------------------------------------------------------------------
  * Path 2 - heatwave metrics.   reference: hdp/metric.py:11-172, 280-369
@@ -122,7 +130,7 @@ int hdp_b200_metrics(const float *d_measure, int64_t C, int64_t T, int64_t ld_t,
                      const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                      const uint8_t *d_is_south,
                      uint16_t *d_out,
-                     void *d_workspace, size_t workspace_bytes, void *stream);
+                     void *d_workspace, size_t workspace_bytes, void *stream, int input_unit /* as for hdp_b200_thresholds */);
 
 /* Test hook: 0 makes k_scan feed every hot run to the definitions' state machines instead of first dropping the runs
  * that cannot change any result (short runs after long breaks, see metric.cu); the outputs must be identical. */
@@ -136,7 +144,7 @@ int hdp_b200_metrics_host(const float *h_measure, int64_t C, int64_t T, int64_t 
                           const int32_t *h_defs, int D,
                           const int32_t *h_season_north, const int32_t *h_season_south, int Y,
                           const uint8_t *h_is_south,
-                          uint16_t *h_out);
+                          uint16_t *h_out, int input_unit);
 
 /* The *_host variants keep their streams, events and device buffers (grown on demand) in a per-device context between
  * calls; this frees them.  Safe to call at any time no *_host call is running. */

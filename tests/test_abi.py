@@ -53,10 +53,11 @@ def test_host_only_entry_points(lib):
         seen.add(msg)
     assert lib.hdp_b200_strerror(0).decode()
     # workspace sizes are pure host arithmetic: positive, monotone in the number of cells, 0 for invalid shapes
-    a = lib.hdp_b200_thresholds_workspace_bytes(64, 10950, 64, 1, 365, 30, 15, 10)
-    b = lib.hdp_b200_thresholds_workspace_bytes(64, 10950, 1, 10950, 365, 30, 15, 10)        # time-contiguous: + the transposed copy
+    a = lib.hdp_b200_thresholds_workspace_bytes(64, 10950, 64, 1, 365, 30, 15, 10, 0)
+    b = lib.hdp_b200_thresholds_workspace_bytes(64, 10950, 1, 10950, 365, 30, 15, 10, 0)     # time-contiguous: + the transposed copy
+    assert lib.hdp_b200_thresholds_workspace_bytes(64, 10950, 64, 1, 365, 30, 15, 10, 1) == b     # Kelvin input: room for a converted copy
     assert 0 < a < b and b - a >= 64 * 10950 * 4
-    assert lib.hdp_b200_thresholds_workspace_bytes(-1, 10950, 64, 1, 365, 30, 15, 10) == 0
+    assert lib.hdp_b200_thresholds_workspace_bytes(-1, 10950, 64, 1, 365, 30, 15, 10, 0) == 0
     m1 = lib.hdp_b200_metrics_workspace_bytes(64, 31390, 64, 1, 365, 10, 6, 86, None)
     m2 = lib.hdp_b200_metrics_workspace_bytes(128, 31390, 128, 1, 365, 10, 6, 86, None)
     assert 0 < m1 < m2

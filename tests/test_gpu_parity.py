@@ -247,6 +247,44 @@ def test_thresholds_network_kernel_many_tiles_and_bad_cells(core):
     assert np.isfinite(got[1::3]).all() and np.isfinite(got[2::3]).all()
 
 
+@pytest.mark.parametrize("units", ["degK", "degF"])
+def test_fused_unit_conversion(core, units, thr_path):
+    # raw Kelvin / Fahrenheit samples handed straight to the kernels (input_unit of the C ABI): bit-identical to converting first
+    # with the host mirror of hdp.measure (pinned against the reference kernel outputs in tests/golden/measure.npz), on every
+    # threshold path, for the hot-day comparison and through the host pipeline; NaN / inf cells included
+    from hdp_b200 import _tables as tb, measure as hm, xr
+    rng = np.random.default_rng(77)
+    base_ax = tb.TimeAxis.date_range("1961-01-01", "1990-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2006-12-31", "noleap")
+    C = 71
+    season = lambda ax: 15 + 10 * np.sin(2 * np.pi * (ax.dayofyr[:, None] - 110) / 365)          # noqa: E731
+    to_raw = (lambda c: c + 273.15) if units == "degK" else (lambda c: c * 1.8 + 32)
+    xb = to_raw(season(base_ax) + 3 * rng.standard_normal((len(base_ax), C))).astype(np.float32)
+    xr_ = to_raw(season(run_ax) + 2 + 3 * rng.standard_normal((len(run_ax), C))).astype(np.float32)
+    xb[rng.integers(0, len(base_ax), 3), 5] = np.nan
+    xb[rng.integers(0, len(base_ax), 3), 6] = np.inf
+    conv = hm.kelvin_to_celsius if units == "degK" else hm.fahrenheit_to_celsius
+    as_da = lambda a: xr.DataArray(a, dims=["time", "cell"], coords={}, name="t", attrs={"units": units})   # noqa: E731
+    cb, cr = xr.values_of(conv(as_da(xb))), xr.values_of(conv(as_da(xr_)))
+    assert cb.dtype == np.float32
+    wt = tb.window_tables(base_ax.dayofyr, 7)
+    q = np.arange(0.9, 1.0, 0.01)
+    want = oracle.thresholds_batch(np.ascontiguousarray(cb), wt.window_samples(), q)
+    got = core.thresholds_array(dev(xb), wt, q, units=units)
+    assert bits_equal(got.cpu().numpy(), want)
+    assert bits_equal(core.thresholds_array(dev(xb.T.copy()).t(), wt, q, units=units).cpu().numpy(), want)    # transposed + converted
+    if thr_path != "default":
+        return
+    assert bits_equal(core.thresholds_host(xb, wt, q, units=units), want)
+    st = tb.hemisphere_ranges(run_ax)
+    thr = np.nan_to_num(want, nan=1e9, posinf=1e9)
+    args = (tb.doy_map(run_ax.dayofyr), [[3, 0, 0], [3, 1, 1], [4, 1, 1]], st.north, st.south, (np.arange(C) % 2).astype(np.uint8))
+    want_met = oracle.metrics_batch(np.ascontiguousarray(cr), thr, *args)
+    out = core.metrics_array(dev(xr_), dev(thr), *args, units=units)
+    assert np.array_equal(ref_layout(out), want_met)
+    assert np.array_equal(core.metrics_host(xr_, thr, *args, units=units).astype(np.int64).transpose(1, 2, 4, 0, 3), want_met)
+
+
 def test_thresholds_errors(core):
     from hdp_b200 import _tables as tb, _lib
     ax = tb.TimeAxis.daily((1961, 1, 1), 2 * 365, "noleap")

@@ -55,10 +55,33 @@ def _stale(target: str, deps: list) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def up_to_date() -> bool:
-    if os.environ.get("HDP_B200_NET_DEV"):
+def _extra_flags(verbose: bool = False) -> list:
+    extra = ["-Xptxas=-v"] if verbose else []
+    if os.environ.get("HDP_B200_NET_DEV"):            # kernel iterations: only four instances of k_thr_net (thr_net.cu) instead of 64
+        extra.append("-DHDP_NET_DEV")
+    return extra
+
+
+def _cmd_of(s: str, extra: list) -> list:
+    return [nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", "-o", _obj_of(s), s]
+
+
+def _same_flags(s: str, extra: list) -> bool:
+    """An object built with other flags is stale whatever its time stamp says."""
+    try:
+        with open(_obj_of(s) + ".cmd") as f:
+            return f.read() == " ".join(_cmd_of(s, extra))
+    except OSError:
         return False
-    return not _stale(LIB, sources() + _common_deps())
+
+
+def up_to_date() -> bool:
+    if _stale(LIB, sources() + _common_deps()):
+        return False
+    if not os.path.isdir(OBJ):                        # a shipped library without its objects (the GPU box): nothing to compare
+        return True
+    extra = _extra_flags()
+    return all(_same_flags(s, extra) for s in sources())
 
 
 def _run(cmd: list, verbose: bool) -> None:
@@ -78,24 +101,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OBJ, exist_ok=True)
     common = _common_deps()
-    extra = ["-Xptxas=-v"] if verbose else []
-    if os.environ.get("HDP_B200_NET_DEV"):            # kernel iterations: only four instances of k_thr_net (thr_net.cu) instead of 64
-        extra.append("-DHDP_NET_DEV")
-    cmd_of = lambda s: [nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", "-o", _obj_of(s), s]      # noqa: E731
-
-    def same_flags(s):                                # an object built with other flags is stale whatever its time stamp says
-        try:
-            with open(_obj_of(s) + ".cmd") as f:
-                return f.read() == " ".join(cmd_of(s))
-        except OSError:
-            return False
-
-    todo = [s for s in sources() if force or _stale(_obj_of(s), [s] + common) or not same_flags(s)]
+    extra = _extra_flags(verbose)
+    todo = [s for s in sources() if force or _stale(_obj_of(s), [s] + common) or not _same_flags(s, _extra_flags())]
 
     def compile_one(s):
-        _run(cmd_of(s), verbose)
+        _run(_cmd_of(s, extra), verbose)
         with open(_obj_of(s) + ".cmd", "w") as f:
-            f.write(" ".join(cmd_of(s)))
+            f.write(" ".join(_cmd_of(s, _extra_flags())))
 
     with ThreadPoolExecutor(max(1, min(len(todo), os.cpu_count() or 1))) as pool:
         list(pool.map(compile_one, todo))

@@ -241,6 +241,43 @@ def to_celsius_array(temp, units: str, out=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# variants the reference declares but does not implement (hdp/threshold.py:105-110), and the figure deck's reduction
+# ----------------------------------------------------------------------------------------------
+
+def thresholds_no_season_array(temps, percentiles: Sequence[float], units=None):
+    """``no_season``: one percentile set per cell over the WHOLE baseline -> f64 ``[C, 1, P]`` (day-of-year axis of length 1;
+    use ``doy_map = zeros(T)`` with :func:`metrics_array`).  Same kernels, same quantile arithmetic, one pooled window."""
+    from ._tables import no_season_tables
+    return thresholds_array(temps, no_season_tables(temps.shape[0]), percentiles, units=units)
+
+
+def fixed_thresholds(n_cells: int, value: float, device="cuda"):
+    """``fixed_value``: the same threshold everywhere and all year -> f64 ``[C, 1, 1]`` (``doy_map = zeros(T)``)."""
+    torch = _torch()
+    return torch.full((int(n_cells), 1, 1), float(value), dtype=torch.float64, device=device)
+
+
+def weighted_spatial_mean(metrics, weights):
+    """``compute_weighted_spatial_mean`` of the reference's figure deck (hdp/graphics/figure.py:14-15) for the metric planes:
+    uint16 ``[..., C]`` and per-cell weights (cos(latitude) of every flattened cell) -> float64 ``[...]``."""
+    torch = _torch()
+    if not (isinstance(metrics, torch.Tensor) and metrics.is_cuda and metrics.dtype == torch.uint16 and metrics.is_contiguous()):
+        raise TypeError("metrics must be a contiguous uint16 CUDA tensor [..., C]")
+    C = int(metrics.shape[-1])
+    w = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float64) if not isinstance(weights, torch.Tensor) else weights)
+    w = w.to(device=metrics.device, dtype=torch.float64).contiguous()
+    if w.numel() != C:
+        raise ValueError("one weight per cell")
+    rows = metrics.numel() // max(C, 1)
+    out = torch.empty(metrics.shape[:-1], dtype=torch.float64, device=metrics.device)
+    with torch.cuda.device(metrics.device):
+        rc = _lib.lib().hdp_b200_weighted_mean(metrics.data_ptr(), rows, C, w.data_ptr(), float(w.sum().item()), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_weighted_mean")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # host-buffer variants (NumPy in, NumPy out; the library pipelines H2D / kernels / D2H over cell chunks)
 # ----------------------------------------------------------------------------------------------
 

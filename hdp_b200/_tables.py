@@ -192,6 +192,13 @@ def window_tables(dayofyr: np.ndarray, window_radius: int) -> WindowTables:
 # Path 2 tables
 # ----------------------------------------------------------------------------------------------
 
+def no_season_tables(n_time: int) -> WindowTables:
+    """The window of the reference's declared-but-unimplemented ``no_season`` option (hdp/threshold.py:105-106: "calculate a
+    single percentile for the entire year"): ONE row that pools every time step.  The kernels take it like any other table
+    (``n_doy = 1``, ``n_y = n_time``, ``W = 1``); the matching day-of-year map is all zeros."""
+    return WindowTables(np.arange(int(n_time), dtype=np.int64).reshape(1, -1), np.zeros((1, 1), np.int64), 0)
+
+
 def doy_map(dayofyr: np.ndarray) -> np.ndarray:
     """``build_doy_map`` (reference hdp/metric.py:265-277): ``dayofyr - 1`` per time step."""
     return np.asarray(dayofyr, dtype=np.int64) - 1

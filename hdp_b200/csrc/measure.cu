@@ -93,6 +93,26 @@ static int launch_measure(const float *temp, const float *rh, int64_t n, int fla
     return HDP_B200_OK;
 }
 
+// Weighted mean over the cells of every row of a uint16 [rows, C] array (the metric planes [4, P, D, Y] x C):
+//     out[row] = sum_c w[c] x[row, c] / sum_c w[c]
+// which is what the reference's figure deck reduces its maps with (hdp/graphics/figure.py:14-15, weights cos(lat)).  One CTA per
+// row; float64 accumulation in a fixed order (thread-strided partial sums, then a tree), so results are reproducible run to run.
+__global__ void __launch_bounds__(256)
+k_weighted_mean(const uint16_t *__restrict__ x, const double *__restrict__ w, int64_t C, double w_sum, double *__restrict__ out)
+{
+    __shared__ double part[256];
+    const uint16_t *row = x + (int64_t)blockIdx.x * C;
+    double acc = 0.0;
+    for (int64_t c = threadIdx.x; c < C; c += 256) acc = __dadd_rn(acc, __dmul_rn(w[c], (double)row[c]));
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] = __dadd_rn(part[threadIdx.x], part[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = __ddiv_rn(part[0], w_sum);
+}
+
 int to_celsius_launch(const float *src, int64_t n, int unit, float *dst, cudaStream_t st)
 {
     if (unit < 0 || unit > 2) return HDP_B200_ERR_INVALID;
@@ -113,6 +133,17 @@ int hdp_b200_heat_index(const float *d_temp_f, const float *d_rh_pct, int64_t n,
 int hdp_b200_heat_index_measure(const float *d_temp_c, const float *d_rh, int64_t n, int rh_is_fraction, float *d_out_c, void *stream)
 {
     return launch_measure<1>(d_temp_c, d_rh, n, rh_is_fraction ? 1 : 0, d_out_c, (cudaStream_t)stream);
+}
+
+int hdp_b200_weighted_mean(const uint16_t *d_x, int64_t rows, int64_t C, const double *d_w, double w_sum, double *d_out, void *stream)
+{
+    if (rows < 0 || C <= 0 || rows > 0x7fffffffLL || !(w_sum > 0.0)) return HDP_B200_ERR_INVALID;
+    if (rows == 0) return HDP_B200_OK;
+    if (!d_x || !d_w || !d_out) return HDP_B200_ERR_INVALID;
+    KernelTimer timer(kMeasure, (cudaStream_t)stream);
+    k_weighted_mean<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(d_x, d_w, C, w_sum, d_out);
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
 }
 
 int hdp_b200_to_celsius(const float *d_temp, int64_t n, int unit, float *d_out_c, void *stream)

@@ -211,10 +211,11 @@ constexpr int kScanQueueWords = 3 * kScanQ * 32;                  // u32 per war
 //
 // Season tables: int4 {start, end, output row, -} per hemisphere, sorted and disjoint within a table
 // (the host splits overlapping tables into several passes, one launch each).
-// (Three CTAs per SM while the accumulator groups fit 80 registers; with more groups - wide definition sweeps - two CTAs and up
-// to 128 registers: the spills of the 80-register build cost more than the lost occupancy.)
+// (Three CTAs per SM for every accumulator-group count: with 24 definitions the 80-register build spills 100 - 400 bytes per
+// thread, but two CTAs with 128 registers and no spills measured SLOWER - 34.0 against 32.1 ms on wide_sweep: the kernel needs
+// the warps more than the registers.)
 template <int NG, int KS, bool kBytes>
-__global__ void __launch_bounds__(kScanWarps * 32, NG <= 4 ? 3 : 2)
+__global__ void __launch_bounds__(kScanWarps * 32, 3)
 k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
        int P, int D, const __grid_constant__ ScanTables tabs, const uint32_t *__restrict__ ge_tab, const uint32_t *__restrict__ brk_tab,
        const int4 *__restrict__ seasons_north, int n_north, const int4 *__restrict__ seasons_south, int n_south, int Y,

@@ -172,6 +172,11 @@ int hdp_b200_heat_index(const float *d_temp_f, const float *d_rh_pct, int64_t n,
 int hdp_b200_heat_index_measure(const float *d_temp_c, const float *d_rh, int64_t n, int rh_is_fraction, float *d_out_c, void *stream);
 int hdp_b200_to_celsius(const float *d_temp, int64_t n, int unit, float *d_out_c, void *stream);
 
+/* Weighted mean over the cells of every row of a u16 [rows, C] array (the metric output is u16 [4 * P * D * Y, C]):
+ * d_out[row] = sum_c d_w[c] * x[row, c] / w_sum, float64, fixed summation order.  With d_w = cos(latitude) this is the
+ * reduction of the reference's figure deck (hdp/graphics/figure.py:14-15 compute_weighted_spatial_mean). */
+int hdp_b200_weighted_mean(const uint16_t *d_x, int64_t rows, int64_t C, const double *d_w, double w_sum, double *d_out, void *stream);
+
 /* Last kernel-launch counters (for bench.py's gpu_launches claim): number of kernels this library has
  * launched since it was loaded. */
 int64_t hdp_b200_launch_count(void);

@@ -6,7 +6,7 @@
 Source lines of the file whose name contains FILE_SUBSTR are grouped into phases: a phase starts at every line matching
 MARKER_REGEX (e.g. '// ---- [0-9A-Z]') inside [first_line, last_line].  Prints, per phase, the share of warp-stall samples,
 executed warp instructions and shared-memory wavefronts (with the ideal, i.e. conflict-free, count)."""
-import csv, io, re, subprocess, sys
+import csv, io, os, re, subprocess, sys
 rep, fsub, marker = sys.argv[1], sys.argv[2], re.compile(sys.argv[3])
 lo, hi = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (0, 10 ** 9)
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
@@ -31,8 +31,11 @@ sec = max(sec, key=lambda s: len(s["rows"]))
 ix = sec["ix"]
 # the report lists code lines only: marker (comment) lines are located in the source file itself
 marks = []
+src_path = sec["file"]
+if not os.path.exists(src_path) and "/hdp_b200/" in src_path:      # captured on the GPU box: same tree, other root
+    src_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hdp_b200", src_path.split("/hdp_b200/", 1)[1])
 try:
-    with open(sec["file"]) as f:
+    with open(src_path) as f:
         marks = [(i + 1, l.strip()[:100]) for i, l in enumerate(f) if marker.search(l)]
 except OSError:
     pass

@@ -679,3 +679,67 @@ def test_host_pipeline_pageable_memory_many_ring_blocks(core):
     xr_t = np.ascontiguousarray(xr_.T).T                                     # time-contiguous host layout
     assert np.array_equal(core.metrics_host(xr_t, thr_h, *args), out_d)
     core.host_release()
+
+
+# ------------------------------------------------------------------------------------------ declared options, reductions, file IO
+def test_no_season_and_fixed_value_variants(core):
+    # the options the reference declares but does not implement (hdp/threshold.py:105-110) as explicit variants on the same
+    # kernels: one window that pools the whole baseline / one constant threshold, with a day-of-year axis of length 1
+    from hdp_b200 import _tables as tb
+    rng = np.random.default_rng(3)
+    ax = tb.TimeAxis.date_range("1961-01-01", "1968-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2005-12-31", "noleap")
+    C = 45
+    x = (15 + 8 * np.sin(2 * np.pi * ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(ax), C))).astype(np.float32)
+    xr_ = (17 + 8 * np.sin(2 * np.pi * run_ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(run_ax), C))).astype(np.float32)
+    q = np.array([0.5, 0.9, 0.99])
+    thr = core.thresholds_no_season_array(dev(x), q)
+    assert tuple(thr.shape) == (C, 1, 3)
+    want = oracle.thresholds_batch(x, tb.no_season_tables(len(ax)).window_samples(), q)
+    assert bits_equal(thr.cpu().numpy(), want)
+    st = tb.hemisphere_ranges(run_ax)
+    zeros = np.zeros(len(run_ax), np.int64)
+    args = ([[3, 0, 0], [3, 1, 1]], st.north, st.south, (np.arange(C) % 2).astype(np.uint8))
+    out = core.metrics_array(dev(xr_), thr, zeros, *args)
+    assert np.array_equal(ref_layout(out), oracle.metrics_batch(xr_, want, zeros, *args))
+    fixed = core.fixed_thresholds(C, 24.5)
+    out = core.metrics_array(dev(xr_), fixed, zeros, *args)
+    assert np.array_equal(ref_layout(out), oracle.metrics_batch(xr_, np.full((C, 1, 1), 24.5), zeros, *args))
+
+
+def test_weighted_spatial_mean(core):
+    # compute_weighted_spatial_mean of the reference's figure deck (hdp/graphics/figure.py:14-15): cos(lat)-weighted mean over cells
+    rng = np.random.default_rng(8)
+    C = 180 * 36
+    lat = np.repeat(-89.5 + np.arange(180), 36)
+    w = np.cos(np.deg2rad(lat))
+    m = torch.as_tensor(rng.integers(0, 154, (4, 3, 2, 7, C)).astype(np.uint16)).cuda()
+    got = core.weighted_spatial_mean(m, w).cpu().numpy()
+    want = (m.cpu().numpy().astype(np.float64) * w).sum(-1) / w.sum()
+    assert got.shape == (4, 3, 2, 7)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)              # float64 sums in a different (fixed) order: tolerance, not bits
+
+
+def test_streaming_io_npy(core, tmp_path):
+    # path in / path out (reference compute_threshold_io / compute_metrics_io): memory-mapped .npy files streamed through the host
+    # pipeline; equals the in-memory path bit for bit; refuses to overwrite like the reference
+    from hdp_b200 import _tables as tb, io as hio
+    rng = np.random.default_rng(4)
+    ax = tb.TimeAxis.date_range("1961-01-01", "1972-12-31", "noleap")
+    run_ax = tb.TimeAxis.date_range("2001-01-01", "2004-12-31", "noleap")
+    C = 130
+    lat = np.linspace(-60, 60, C)
+    xb = (288 + 8 * np.sin(2 * np.pi * ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(ax), C))).astype(np.float32)     # Kelvin
+    xr_ = (290 + 8 * np.sin(2 * np.pi * run_ax.dayofyr[:, None] / 365) + 3 * rng.standard_normal((len(run_ax), C))).astype(np.float32)
+    np.save(tmp_path / "base.npy", xb); np.save(tmp_path / "run.npy", xr_)
+    q = np.arange(0.9, 1.0, 0.02)
+    defs = [[3, 0, 0], [4, 1, 1]]
+    hio.compute_threshold_io(str(tmp_path / "base.npy"), ax, str(tmp_path / "thr.npy"), q, units="degK")
+    with pytest.raises(FileExistsError):
+        hio.compute_threshold_io(str(tmp_path / "base.npy"), ax, str(tmp_path / "thr.npy"), q, units="degK")
+    hio.compute_metrics_io(str(tmp_path / "run.npy"), run_ax, str(tmp_path / "thr.npy"), lat, str(tmp_path / "met.npy"), defs, units="degK")
+    thr = core.thresholds_array(dev(xb), tb.window_tables(ax.dayofyr, 7), q, units="degK")
+    assert bits_equal(np.load(tmp_path / "thr.npy"), thr.cpu().numpy())
+    st = tb.hemisphere_ranges(run_ax)
+    out = core.metrics_array(dev(xr_), thr, tb.doy_map(run_ax.dayofyr), defs, st.north, st.south, tb.is_south(lat), units="degK")
+    assert np.array_equal(np.load(tmp_path / "met.npy"), out.cpu().numpy())

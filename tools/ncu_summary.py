@@ -24,7 +24,7 @@ for r in rd[1:]:
     t = tot.setdefault(name, [0, 0.0]); t[0] += 1; t[1] += v
 allms = sum(t[1] for t in tot.values())
 with open(os.path.join(prof, f"{tag}_launches.txt"), "w") as f:
-    f.write(f"# ncu launch list of `python bench.py --no-e2e --no-cpu --steps 1 --warmup 1` (warm-up step + timed step, all launches),\n"
+    f.write(f"# ncu launch list of `python bench.py --no-e2e --no-cpu --no-extra --steps 1 --warmup 1` (warm-up step + timed step, all launches),\n"
             f"# --metrics gpu__time_duration.sum --clock-control none; per-launch times are serialised and cold-cache: compare SHARES\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'total ms':>10s} {'ms/launch':>10s} {'share':>7s}\n")
     for k, (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):

@@ -6,7 +6,7 @@
 #   prof_TAG_{net,hot,scan}.ncu-rep   one `--set full` capture of the first launch of each kernel (full 64 800-cell grid)
 # Numbers printed under ncu are never bench values.
 TAG=$1
-CMD="python bench.py --no-e2e --no-cpu --steps 1 --warmup 1"
+CMD="python bench.py --no-e2e --no-cpu --no-extra --steps 1 --warmup 1"
 $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_|hdp" -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 for k in net:k_thr_net hot:k_hot_words scan:k_scan; do

@@ -214,7 +214,10 @@ constexpr int kScanQueueWords = 3 * kScanQ * 32;                  // u32 per war
 // (Three CTAs per SM for every accumulator-group count: with 24 definitions the 80-register build spills 100 - 400 bytes per
 // thread, but two CTAs with 128 registers and no spills measured SLOWER - 34.0 against 32.1 ms on wide_sweep: the kernel needs
 // the warps more than the registers.)
-template <int NG, int KS, bool kBytes>
+// LMIN / BMAX > = 0: the run filter's two constants (smallest min_duration, largest max_break of the definition set) at compile
+// time, which unrolls its shift loops completely - 12 % of the kernel on the reference's documented definitions (README.md:51:
+// min duration 3 .. 5, at most one break day: LMIN = 3, BMAX = 1).  LMIN = 0: run-time values (any definition set).
+template <int NG, int KS, bool kBytes, int LMIN = 0, int BMAX = 0>
 __global__ void __launch_bounds__(kScanWarps * 32, 3)
 k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__restrict__ words,
        int P, int D, const __grid_constant__ ScanTables tabs, const uint32_t *__restrict__ ge_tab, const uint32_t *__restrict__ brk_tab,
@@ -334,19 +337,19 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
     uint32_t tail = 0u, a_tail = 0u;                              // hot days / `long` seeds of the 32 days before word k_ext (bit 31 = yesterday)
     uint32_t live_in = 0u, open_f = 0u;                           // a live cluster / a kept run reaches the end of the previous word
     uint32_t qr = 0u, qw = 0u;                                    // ring buffer read / write counters
-    const bool f_on = tabs.f_on != 0;
-    const int f_lmin = tabs.f_lmin, f_bmax = tabs.f_bmax;
+    const bool f_on = LMIN > 0 || tabs.f_on != 0;
+    const int f_lmin = LMIN > 0 ? LMIN : tabs.f_lmin, f_bmax = LMIN > 0 ? BMAX : tabs.f_bmax;
 
-    auto extract = [&](int n_words, bool live) {
-        for (int i = 0; i < n_words; i++) {
+    // one word: `cur` = word k_ext of this lane's cell, `nxt` = word k_ext + 1
+    auto extract_word = [&](const uint32_t cur, const uint32_t nxt, bool live) {
+        {
             const uint4 wm = lds_v4(meta_a + 16u * (uint32_t)k_ext);   // warp-uniform
             const int t0 = (int)wm.x, nb = (int)wm.y;
-            const uint32_t cur = w0;
             const uint32_t vmask = 0xffffffffu >> (32 - nb);
             uint32_t keep = cur;
             if (f_on) {
                 // E = the 64 days starting at this word (lo, hi): the next word follows at bit nb
-                const uint32_t fut = w1 | (uint32_t)wm.z;
+                const uint32_t fut = nxt | (uint32_t)wm.z;
                 uint32_t lo = cur, hi = fut;
                 if (nb < 32) {                                     // warp-uniform
                     lo = cur | (fut << nb);
@@ -386,11 +389,31 @@ k_scan(const uint32_t *__restrict__ hot, int64_t C, int K, int T, const int4 *__
                 sts_u32(slot, st); sts_u32(slot + kQEn, en); sts_u32(slot + kQT0, (uint32_t)t0);
                 qw++;
             }
-            w0 = w1; w1 = w2; w2 = w3;
-            w3 = k_ext + 4 < K ? __ldg(hp_ahead) : 0u;            // (words past the end read as cold)
-            if (k_ext + 4 + kScanQ < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp_ahead + pf_off));   // the next burst's words
-            hp_ahead += C;
-            k_ext++;
+        }
+    };
+    // word k_ext + 4 (words past the end read as cold); the L2 prefetch reaches for the next burst's words
+    auto next_word = [&]() -> uint32_t {
+        const uint32_t v = k_ext + 4 < K ? __ldg(hp_ahead) : 0u;
+        if (k_ext + 4 + kScanQ < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp_ahead + pf_off));
+        hp_ahead += C;
+        k_ext++;
+        return v;
+    };
+    // Four words per round with the registers taking turns, so that a word fetched now is not touched before it is needed four
+    // words later (rotating w0 <- w1 <- w2 <- w3 reads the register a load is still in flight for: the whole warp then waits for
+    // every word - 11 % of this kernel's stall samples in round 1's profile); the rotation is left to the last < 4 words of a burst.
+    auto extract = [&](int n_words, bool live) {
+        int i = 0;
+        for (; i + 4 <= n_words; i += 4) {
+            extract_word(w0, w1, live); w0 = next_word();
+            extract_word(w1, w2, live); w1 = next_word();
+            extract_word(w2, w3, live); w2 = next_word();
+            extract_word(w3, w0, live); w3 = next_word();
+        }
+        for (; i < n_words; i++) {
+            extract_word(w0, w1, live);
+            const uint32_t v = next_word();
+            w0 = w1; w1 = w2; w2 = w3; w3 = v;
         }
     };
 
@@ -758,9 +781,21 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
             k_scan<NG, KS, BY><<<scan_grid, kScanWarps * 32, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, brk_tab, \
                                                                               sn, nn, ss, ns, Y, d_is_south, d_out);     \
         } while (0)
+#define HDP_LAUNCH_SCAN_F(NG, BY, LM, BM)                                                                                \
+        do {                                                                                                             \
+            HDP_CUDA_TRY(cudaFuncSetAttribute(k_scan<NG, 1, BY, LM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem)); \
+            k_scan<NG, 1, BY, LM, BM><<<scan_grid, kScanWarps * 32, scan_smem, st>>>(L.hot, C, K, (int)T, L.words, P, D, tabs, ge_tab, \
+                                                                                     brk_tab, sn, nn, ss, ns, Y, d_is_south, d_out); \
+        } while (0)
 #define HDP_SCAN_KS(NG, BY)                                                \
         switch (ks) {                                                      \
-        case 1: HDP_LAUNCH_SCAN(NG, 1, BY); break;                         \
+        case 1:                                                            \
+            /* compile-time filter constants for the usual shapes (seasons of at most 255 days, common definition sets) */ \
+            if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 1) HDP_LAUNCH_SCAN_F(NG, true, 3, 1);       \
+            else if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 0) HDP_LAUNCH_SCAN_F(NG, true, 3, 0);  \
+            else if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 2) HDP_LAUNCH_SCAN_F(NG, true, 3, 2);  \
+            else HDP_LAUNCH_SCAN(NG, 1, BY);                               \
+            break;                                                         \
         case 2: HDP_LAUNCH_SCAN(NG, 2, BY); break;                         \
         case 4: HDP_LAUNCH_SCAN(NG, 4, BY); break;                         \
         case 16: HDP_LAUNCH_SCAN(NG, 16, BY); break;                       \
@@ -786,6 +821,7 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
             }
         }
 #undef HDP_SCAN_KS
+#undef HDP_LAUNCH_SCAN_F
 #undef HDP_LAUNCH_SCAN
         HDP_LAUNCH_CHECK();
     }

@@ -92,12 +92,13 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
     if (nd < kTileDoy || Ppad != P)
         for (int i = tid; i < (Ppad / PG) * kTileDoy * PG * kTilePad; i += 256) thr_s[i] = __int_as_float(0x7f800000);
     __syncthreads();
-    for (int e0 = 0; e0 < n_el; e0 += 32 * kFillLoads) {
+    const float inv_p = 1.0f / (float)P;                   // e / P for e < 1024, P <= 32: (e + 0.5) / P is >= 1 / 64 away from every
+    for (int e0 = 0; e0 < n_el; e0 += 32 * kFillLoads) {   // integer, far more than the error of the float product
         int dst[kFillLoads];
 #pragma unroll
         for (int i = 0; i < kFillLoads; i++) {
             const int e = e0 + 32 * i + lane;
-            const int j = e / P, p = e - j * P, g = p / PG, q = p - g * PG;
+            const int j = __float2int_rz(((float)e + 0.5f) * inv_p), p = e - j * P, g = p / PG, q = p - g * PG;
             dst[i] = e < n_el ? ((g * kTileDoy + j) * PG + q) * kTilePad : -1;
         }
         for (int cell = warp; cell < kTileCells; cell += 8) {
@@ -120,6 +121,7 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
     // thresholds, which are read from shared memory into registers once per kHotYears samples.  Bits are collected at
     // the day's position inside the 32-day block (an immediate) and shifted to the word's own origin when stored.
     const int w_begin = blk_start[db], w_end = blk_start[db + 1];
+    const int64_t plane_words = (int64_t)K * C;
     for (int i0 = w_begin + warp * kHotYears; i0 < w_end; i0 += 8 * kHotYears) {
         int kk[kHotYears], jo[kHotYears], nb[kHotYears];
         const float *xp[kHotYears];
@@ -141,13 +143,16 @@ k_hot_words(const float *__restrict__ x, int64_t C, int64_t ld_t,
 #pragma unroll
                 for (int q = 0; q < PG; q++) m[y][q] = 0u;
             const float *ts = thr_s + (size_t)(pg / PG) * (kTileDoy * PG * kTilePad) + lane;
+            uint32_t *hp[kHotYears];                               // word kk[y] of percentile pg of this cell; percentile planes are K * C words apart
+#pragma unroll
+            for (int y = 0; y < kHotYears; y++) hp[y] = hot + ((int64_t)pg * K + kk[y]) * C + c;
             hot_half<PG, 0, UNIT>(m, xp, jo, nb, ld_t, ts);
             if (j_hi > kHotDays) hot_half<PG, kHotDays, UNIT>(m, xp, jo, nb, ld_t, ts);      // warp-uniform
 #pragma unroll
             for (int y = 0; y < kHotYears; y++)
 #pragma unroll
                 for (int q = 0; q < PG; q++)
-                    if (nb[y] > 0 && pg + q < P) hot[((int64_t)(pg + q) * K + kk[y]) * C + c] = m[y][q] >> jo[y];
+                    if (nb[y] > 0 && pg + q < P) hp[y][(int64_t)q * plane_words] = m[y][q] >> jo[y];
         }
     }
 }

@@ -25,6 +25,7 @@ SIGNATURES = {
     "hdp_b200_thresholds_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _int, _int, _int, _int]),
     "hdp_b200_thresholds": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p, _sz, _p, _int]),
     "hdp_b200_thresholds_force_generic": (None, [_int]),
+    "hdp_b200_thresholds_kernel_choice": (_int, [_p, _p, _i64, _int, _int, _int, _p, _int, _p]),
     "hdp_b200_thresholds_host": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _int, _int, _int, _p, _int, _p, _p, _int]),
     "hdp_b200_metrics_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _int, _int, _int, _int, _p]),
     "hdp_b200_metrics": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _int, _p, _p, _p, _sz, _p, _int]),

@@ -1761,6 +1761,37 @@ struct ThrPlans {
     SelTable sel;
 };
 
+// Plans of the (tables, quantiles) pair, built once and shared (host only: no CUDA call).
+static std::shared_ptr<ThrPlans> thr_plans(const int32_t *h_time_index, const int32_t *h_win_rows, int64_t T_b, int n_doy, int n_y, int W,
+                                           const double *h_q, int P, int64_t C)
+{
+    static std::mutex plan_mu;
+    static std::shared_ptr<ThrPlans> cached;
+    std::lock_guard<std::mutex> plan_lock(plan_mu);
+    const int64_t b = (int64_t)W * n_y;
+    const size_t n_ti = (size_t)n_doy * n_y, n_wr = (size_t)n_doy * W;
+    const bool same = cached && cached->dims[0] == n_doy && cached->dims[1] == n_y && cached->dims[2] == W && cached->dims[3] == T_b &&
+                      cached->rows.size() == n_wr && std::equal(cached->rows.begin(), cached->rows.end(), h_win_rows) &&
+                      cached->ti.size() == n_ti && std::equal(cached->ti.begin(), cached->ti.end(), h_time_index) &&
+                      cached->q.size() == (size_t)P && std::equal(cached->q.begin(), cached->q.end(), h_q);
+    if (!same) {
+        auto fresh = std::make_shared<ThrPlans>();
+        plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, fresh->ranked);
+        plan_seg(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->seg);
+        fill_sel(fresh->sel, b, h_q, P);
+        int is_max[HDP_B200_MAX_PERCENTILES], is_interp[HDP_B200_MAX_PERCENTILES];
+        for (int p = 0; p < P; p++) { is_max[p] = fresh->sel.mode[p] == kSelMax; is_interp[p] = fresh->sel.mode[p] == kSelInterp; }
+        net_plan(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->sel.pos_lo, fresh->sel.pos_hi, is_max, is_interp,
+                 fresh->sel.w_lo, fresh->sel.w_hi, P, C, fresh->net);
+        fresh->rows.assign(h_win_rows, h_win_rows + n_wr);
+        fresh->ti.assign(h_time_index, h_time_index + n_ti);
+        fresh->q.assign(h_q, h_q + P);
+        fresh->dims[0] = n_doy; fresh->dims[1] = n_y; fresh->dims[2] = W; fresh->dims[3] = T_b;
+        cached = fresh;
+    }
+    return cached;
+}
+
 // The whole of hdp_b200_thresholds.  `carve_cells` sizes the workspace layout (>= C; the host pipeline passes its chunk
 // capacity so that every chunk sees the tables at the same place) and `tables_resident` skips the table uploads when
 // the previous call on this workspace and stream used identical tables.
@@ -1815,33 +1846,7 @@ int thresholds_launch(const float *d_temps, int64_t C, int64_t T_b, int64_t ld_t
     };
     if (!tables_resident) HDP_CUDA_TRY(cudaMemcpyAsync(L.time_index, h_time_index, sizeof(int) * (size_t)n_doy * n_y, cudaMemcpyHostToDevice, st));
 
-    std::shared_ptr<ThrPlans> plans;
-    {
-        static std::mutex plan_mu;
-        static std::shared_ptr<ThrPlans> cached;
-        std::lock_guard<std::mutex> plan_lock(plan_mu);
-        const size_t n_ti = (size_t)n_doy * n_y, n_wr = (size_t)n_doy * W;
-        const bool same = cached && cached->dims[0] == n_doy && cached->dims[1] == n_y && cached->dims[2] == W && cached->dims[3] == T_b &&
-                          cached->rows.size() == n_wr && std::equal(cached->rows.begin(), cached->rows.end(), h_win_rows) &&
-                          cached->ti.size() == n_ti && std::equal(cached->ti.begin(), cached->ti.end(), h_time_index) &&
-                          cached->q.size() == (size_t)P && std::equal(cached->q.begin(), cached->q.end(), h_q);
-        if (!same) {
-            auto fresh = std::make_shared<ThrPlans>();
-            plan_ranked(h_win_rows, n_doy, n_y, W, h_q, P, fresh->ranked);
-            plan_seg(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->seg);
-            fill_sel(fresh->sel, b, h_q, P);
-            int is_max[HDP_B200_MAX_PERCENTILES], is_interp[HDP_B200_MAX_PERCENTILES];
-            for (int p = 0; p < P; p++) { is_max[p] = fresh->sel.mode[p] == kSelMax; is_interp[p] = fresh->sel.mode[p] == kSelInterp; }
-            net_plan(h_time_index, h_win_rows, T_b, n_doy, n_y, W, fresh->sel.pos_lo, fresh->sel.pos_hi, is_max, is_interp,
-                     fresh->sel.w_lo, fresh->sel.w_hi, P, C, fresh->net);
-            fresh->rows.assign(h_win_rows, h_win_rows + n_wr);
-            fresh->ti.assign(h_time_index, h_time_index + n_ti);
-            fresh->q.assign(h_q, h_q + P);
-            fresh->dims[0] = n_doy; fresh->dims[1] = n_y; fresh->dims[2] = W; fresh->dims[3] = T_b;
-            cached = fresh;
-        }
-        plans = cached;
-    }
+    std::shared_ptr<ThrPlans> plans = thr_plans(h_time_index, h_win_rows, T_b, n_doy, n_y, W, h_q, P, C);
     const RankedPlan &plan = plans->ranked;
     const SegPlan &seg = plans->seg;
     const int E = n_doy * n_y;
@@ -1964,6 +1969,26 @@ void hdp_b200_thresholds_force_generic(int on)
 {
     g_force_generic = on == 1; g_force_ranked = on == 2; g_seg_candidates = on != 3; g_seg_light = on != 4; g_net = on != 5;
     g_net_tmem = on != 6;
+}
+
+int hdp_b200_thresholds_kernel_choice(const int32_t *h_time_index, const int32_t *h_win_rows, int64_t T_b, int n_doy, int n_y, int W,
+                                      const double *h_q, int P, int *info)
+{
+    if (bad_dims(1, T_b, n_doy, n_y, W, P) || !h_time_index || !h_win_rows || !h_q || !info) return HDP_B200_ERR_INVALID;
+    if (P > HDP_B200_MAX_PERCENTILES || (int64_t)W * n_y > HDP_B200_MAX_WINDOW) return HDP_B200_ERR_UNSUPPORTED;
+    const auto plans = thr_plans(h_time_index, h_win_rows, T_b, n_doy, n_y, W, h_q, P, 64800);
+    const NetGeom &g = plans->net.geo;
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    if (plans->seg.usable && plans->net.usable) {
+        info[0] = 4; info[1] = g.NY; info[2] = g.K; info[3] = g.M; info[4] = g.s; info[5] = g.n_irr; info[6] = g.tm_warps; info[7] = g.tm_lists;
+    } else if (plans->seg.usable) {
+        int kmin = W * n_y - 1;
+        for (int p = 0; p < P; p++) kmin = std::min(kmin, plans->sel.pos_lo[p]);
+        const int m = (W * n_y - kmin + W - 1) / W;
+        info[0] = (m <= kSegCandTop && 3 * m <= n_y) ? 3 : 2;
+        info[4] = plans->seg.geo.S;
+    } else if (plans->ranked.usable) info[0] = 1;
+    return HDP_B200_OK;
 }
 
 size_t hdp_b200_thresholds_workspace_bytes(int64_t C, int64_t T_b, int64_t ld_t, int64_t ld_c,

@@ -96,6 +96,14 @@ int hdp_b200_thresholds(const float *d_temps, int64_t C, int64_t T_b, int64_t ld
  * list in shared memory (no tensor-memory variant k_thr_net_tm). */
 void hdp_b200_thresholds_force_generic(int on);
 
+/* Which kernel hdp_b200_thresholds would run for these tables and quantiles (host logic only: no device needed).
+ * info[0] = 0 k_thr_generic, 1 k_thr_ranked, 2 k_thr_seg, 3 k_thr_cand + k_thr_seg, 4 k_thr_net; for k_thr_net info[1..7] =
+ * {samples per row (padded), list length K, blocks per window, rows per block, irregular days, warps per CTA of the
+ * tensor-memory variant (0 = shared memory only), suffix lists kept in tensor memory}; for the segment kernels info[4] = days
+ * per segment. */
+int hdp_b200_thresholds_kernel_choice(const int32_t *h_time_index, const int32_t *h_win_rows, int64_t T_b, int n_doy, int n_y, int W,
+                                      const double *h_q, int P, int *info);
+
 /* Host-buffer variant (chunked H2D / kernels / D2H pipeline, see csrc/host.cu).  d_keep: optional DEVICE buffer
  * f64 [C, n_doy, P]; when given, the thresholds are also left there, so that the metric pass that follows
  * (hdp_b200_metrics_host with d_thr = d_keep) does not upload them again - in the reference workflow

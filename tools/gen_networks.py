@@ -132,29 +132,33 @@ def best_merge(k, nb):
 
 
 def evaluate(ops, outs, env):
+    """Runs a network on many input vectors at once: env maps input names to NumPy arrays of one value per test case."""
+    import numpy as np
     env = dict(env)
     for dst, op, a, b in ops:
-        env[dst] = max(env[a], env[b]) if op == "max" else min(env[a], env[b])
-    return [env[o] if o is not NEG else float("-inf") for o in outs]
+        env[dst] = np.maximum(env[a], env[b]) if op == "max" else np.minimum(env[a], env[b])
+    n = len(next(iter(env.values())))
+    return np.stack([env[o] if o is not NEG else np.full(n, -np.inf) for o in outs], axis=1)
 
 
 def check_sort(n, ops, outs, rng):
-    for _ in range(300):
-        vals = [rng.choice([0, 1]) for _ in range(n)] if rng.random() < 0.5 else [rng.randrange(0, 40) for _ in range(n)]
-        got = evaluate(ops, outs, {f"v[{i}]": vals[i] for i in range(n)})
-        assert got == sorted(vals, reverse=True), (n, vals, got)
+    import numpy as np
+    gen = np.random.default_rng(rng.randrange(1 << 30))
+    vals = np.concatenate([gen.integers(0, 2, (4000, n)), gen.integers(0, 40, (2000, n)), gen.permuted(np.tile(np.arange(n), (2000, 1)), axis=1)])
+    got = evaluate(ops, outs, {f"v[{i}]": vals[:, i].astype(float) for i in range(n)})
+    assert np.array_equal(got, -np.sort(-vals.astype(float), axis=1)), n
 
 
 def check_merge(k, nb, ops, outs):
-    # 0/1 principle restricted to sorted inputs: every (number of ones in a, number of ones in b) pair
-    for ones_a in range(k + 1):
-        for ones_b in range(nb + 1):
-            a = [1] * ones_a + [0] * (k - ones_a)
-            b = [1] * ones_b + [0] * (nb - ones_b)
-            env = {f"a[{i}]": a[i] for i in range(k)}
-            env.update({f"b[{i}]": b[i] for i in range(nb)})
-            got = evaluate(ops, outs, env)
-            assert got == sorted(a + b, reverse=True)[:k], (k, nb, ones_a, ones_b)
+    # 0/1 principle restricted to sorted inputs: every (number of ones in a, number of ones in b) pair, all at once
+    import numpy as np
+    oa, ob = np.meshgrid(np.arange(k + 1), np.arange(nb + 1), indexing="ij")
+    oa, ob = oa.ravel(), ob.ravel()
+    env = {f"a[{i}]": (oa > i).astype(float) for i in range(k)}
+    env.update({f"b[{i}]": (ob > i).astype(float) for i in range(nb)})
+    got = evaluate(ops, outs, env)
+    want = (np.arange(k)[None, :] < (oa + ob)[:, None]).astype(float)       # the k largest of oa + ob ones and the rest zeros
+    assert np.array_equal(got, want), (k, nb)
 
 
 SORTS = [8, 16, 24, 30, 32]

@@ -67,6 +67,12 @@ def _year_times(years: np.ndarray, calendar: str):
     return _tables.TimeAxis(np.asarray(years, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), np.ones(n, np.int64), calendar)
 
 
+# dtype of the metric variables.  The reference's are int64 (hdp/tests/test_workflow.py:57) and so is the default; at CMIP scale that
+# widening is 10.7 GB per measure and the largest single cost of the drop-in call (tools/api_e2e.py).  A caller that can live with
+# the library's native encoding sets `hdp_b200.metric.METRIC_DTYPE = np.uint16` (values are <= the longest season, < 65536).
+METRIC_DTYPE = np.int64
+
+
 def _widen_int64(a: np.ndarray) -> np.ndarray:
     """uint16 -> int64 of one metric plane ([P, D, Y, C], C-contiguous).  The reference's metrics are int64
     (hdp/tests/test_workflow.py:57); at CMIP scale that is 2.7 GB in and 10.7 GB out per measure, so the widening is split
@@ -131,7 +137,7 @@ def compute_individual_metrics(measure, threshold, hw_definitions: list, include
     dims = ["percentile", "definition", *cell_dims, "time"]
     data_vars = {}
     for i, name in enumerate(_core.METRIC_NAMES):                   # HWF=0, HWN=1, HWD=2, HWA=3, :454-461
-        wide = _widen_int64(out[i])                                 # [P, D, Y, C] uint16 -> int64, the reference's dtype
+        wide = out[i] if np.dtype(METRIC_DTYPE) == np.uint16 else _widen_int64(out[i]).astype(METRIC_DTYPE, copy=False)   # [P, D, Y, C]
         plane = wide.transpose(0, 1, 3, 2).reshape(P, D, *cell_shape, Y)                # view: no host transposition
         data_vars[name] = xr.DataArray(plane, dims=dims, coords=coords)
     ds = xr.Dataset(data_vars)

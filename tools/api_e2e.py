@@ -37,3 +37,8 @@ for rep in range(2):
           f"-> {cy / (t3 - t0):.3g} cell-years/s through the Python API", flush=True)
 name = "tas.tas_threshold.HWF"
 print(name, met[name].shape, met[name].dtype, float(np.asarray(xr.values_of(met[name])).mean()))
+# the same with the library's native metric encoding (no int64 widening)
+metric.METRIC_DTYPE = np.uint16
+t2 = time.perf_counter()
+met = metric.compute_group_metrics(run_m, thr, wl.defs)
+print(f"METRIC_DTYPE = uint16: compute_group_metrics {time.perf_counter() - t2:.2f} s", met[name].dtype, flush=True)

@@ -9,7 +9,10 @@ executed warp instructions and shared-memory wavefronts (with the ideal, i.e. co
 import csv, io, os, re, subprocess, sys
 rep, fsub, marker = sys.argv[1], sys.argv[2], re.compile(sys.argv[3])
 lo, hi = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (0, 10 ** 9)
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):                                           # an exported `--page source --print-source cuda,sass --csv`
+    txt = open(rep).read()
+else:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 def num(x):
     try: return float(x)

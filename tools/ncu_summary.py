@@ -50,9 +50,13 @@ md = [f"# {tag}: `ncu --set full --clock-control none --import-source on`, first
       "Reports: gpurun_out/prof_%s_{net,hot,scan}.ncu-rep (not tracked); numbers copied from `ncu -i ... --page raw --csv`.\n" % tag]
 for short in ("net", "cand", "seg", "hot", "scan"):
     rep = os.path.join(out, f"prof_{tag}_{short}.ncu-rep")
-    if not os.path.exists(rep):
+    raw_csv = os.path.join(out, f"raw_{tag}_{short}.csv")          # written on the GPU box by profile_round.sh (the report itself is dropped there)
+    if os.path.exists(raw_csv):
+        txt = open(raw_csv).read()
+    elif os.path.exists(rep):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(txt)))
     hh, units, vals = rr[0], rr[1], rr[2]
     name = vals[hh.index("Kernel Name")].split("(")[0].replace("void ", "")

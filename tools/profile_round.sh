@@ -11,6 +11,12 @@ $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_|hdp" -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 for k in net:k_thr_net hot:k_hot_words scan:k_scan; do
   short=${k%%:*}; name=${k##*:}
-  ncu --set full --clock-control none --import-source on -k regex:"$name" -c 1 -f -o gpurun_out/prof_${TAG}_$short $CMD > gpurun_out/ncu_${TAG}_$short.log 2>&1
+  # (sources are imported for the threshold kernel only: with them the three reports exceed what gpurun carries back)
+  SRC=""; [ "$short" = "net" ] && SRC="--import-source on"
+  ncu --set full --clock-control none $SRC -k regex:"$name" -c 1 -f -o gpurun_out/prof_${TAG}_$short $CMD > gpurun_out/ncu_${TAG}_$short.log 2>&1
+  # every report embeds the library's whole cubin (~30 MB): keep its pages as CSV and drop it, or the three exceed what gpurun carries back
+  ncu -i gpurun_out/prof_${TAG}_$short.ncu-rep --page raw --csv > gpurun_out/raw_${TAG}_$short.csv 2>/dev/null
+  [ "$short" = "net" ] && ncu -i gpurun_out/prof_${TAG}_$short.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/src_${TAG}_$short.csv 2>/dev/null
+  rm -f gpurun_out/prof_${TAG}_$short.ncu-rep
 done
 ls -la gpurun_out/*$TAG*

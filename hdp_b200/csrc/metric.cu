@@ -763,7 +763,7 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
     const int per = bytes ? 4 : 2;
     int ng = (D + per - 1) / per;
     ng = ng <= 2 ? 2 : ng <= 3 ? 3 : ng <= 4 ? 4 : ng <= 6 ? 6 : ng <= 8 ? 8 : ng <= 12 ? 12 : 16;
-    const int ks = ks_needed <= 1 ? 1 : ks_needed <= 2 ? 2 : ks_needed <= 4 ? 4 : ks_needed <= 16 ? 16 : 32;
+    const int ks = ks_needed <= 1 ? 1 : ks_needed <= 2 ? 2 : 32;      // bit planes of the max_subs counters: 1, 2 or all 32
 
     // all passes of both hemispheres live side by side in the workspace: north passes, then south passes
     std::vector<int4> tab;
@@ -797,13 +797,10 @@ int metrics_launch(const float *d_measure, int64_t C, int64_t T, int64_t ld_t, i
         case 1:                                                            \
             /* compile-time filter constants for the usual shapes (seasons of at most 255 days, common definition sets) */ \
             if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 1) HDP_LAUNCH_SCAN_F(NG, true, 3, 1);       \
-            else if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 0) HDP_LAUNCH_SCAN_F(NG, true, 3, 0);  \
             else if (BY && tabs.f_on && tabs.f_lmin == 3 && tabs.f_bmax == 2) HDP_LAUNCH_SCAN_F(NG, true, 3, 2);  \
             else HDP_LAUNCH_SCAN(NG, 1, BY);                               \
             break;                                                         \
         case 2: HDP_LAUNCH_SCAN(NG, 2, BY); break;                         \
-        case 4: HDP_LAUNCH_SCAN(NG, 4, BY); break;                         \
-        case 16: HDP_LAUNCH_SCAN(NG, 16, BY); break;                       \
         default: HDP_LAUNCH_SCAN(NG, 32, BY); break;                       \
         }
         if (bytes) {

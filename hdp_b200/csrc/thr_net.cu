@@ -201,8 +201,10 @@ struct SlotsMixed {                                               // suffix list
     }
 };
 
-// One work item = (32-cell tile, chunk of super-steps) or (tile, the irregular days), worked through by ONE warp.
-template <int NY, int K, int M, bool kPads, class Slots>
+// One work item, worked through by ONE warp: (32-cell tile, chunk of super-steps) of the block schedule, or - kProg, a kernel of its
+// own (k_thr_net_irr), so that the hot loop of the regular items carries none of its branches - the tile's irregular days, which
+// follow a PROGRAM built by net_plan (item = tile).
+template <int NY, int K, int M, bool kPads, bool kProg, class Slots>
 __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const float *__restrict__ x, int64_t C, uint32_t ld_t,
                                          const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day,
                                          const int *__restrict__ irr_time, const NetGeom &g, const NetSel &sel, double *__restrict__ out,
@@ -210,9 +212,8 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
 {
     static_assert(NY <= 32, "one lane per time index of a row");
     const int lane = threadIdx.x & 31;
-    const int64_t n_regular = g.n_tiles * g.n_chunks;
-    const bool irregular = item >= n_regular;
-    const int64_t tile = irregular ? item - n_regular : item / g.n_chunks;
+    constexpr bool irregular = kProg;
+    const int64_t tile = irregular ? item : item / g.n_chunks;
     const int chunk = irregular ? 0 : (int)(item - tile * g.n_chunks);
     const int64_t c = tile * 32 + lane;
     const bool valid = c < C;
@@ -223,8 +224,9 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
     const int ty = lane < NY ? lane : NY - 1;
 
     const int b0 = chunk * g.steps_per_chunk, b1 = min(b0 + g.steps_per_chunk, g.n_steps);
-    const int n_rows = irregular ? g.n_irr * g.W : (kPro + 2 * (b1 - b0)) * s;
-    const int per = irregular ? g.W : s;
+    const int n_rows = irregular ? g.n_irr_steps : (kPro + 2 * (b1 - b0)) * s;
+    const int per = irregular ? 0x7fffffff : s;
+    const int4 *prog = (const int4 *)irr_day;                     // kProg: what every row step does
 
     // the row table of step n = (pb, it): block phase and row inside it
     auto row_table = [&](int n, int pb, int it) -> const int * {
@@ -273,8 +275,9 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
         NetStepDesc d{it == 0 ? kStartEmpty : -1, -1, -1, -1, -1};
         const int *emit_from = nullptr;
         bool window_of_prefix = false;
+        int4 pg = make_int4(0, 0, -1, 0);
         if (irregular) {
-            if (it == per - 1) emit_from = irr_day + pb;
+            pg = __ldg(prog + n);
         } else if (pb < kPro) {
             if (it == s - 1) {
                 d.store_run = slot_f;
@@ -298,6 +301,21 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
 
         // ---- order the row, merge it into the running list
         net::Sort<NY>::run(v);
+        if (irregular) {
+            d.start = (pg.x & 1) ? kStartEmpty : -1;
+            d.other = (pg.y & 0xff) - 1;
+            d.store_run = ((pg.y >> 8) & 0xff) - 1;
+            if (pg.x & 2) {                                       // a row that joins this window only: merged into a copy, the chain goes on without it
+                float tmp[K];
+#pragma unroll
+                for (int e = 0; e < K; e++) tmp[e] = run[e];
+                net::Merge<K, NY>::run(tmp, v);
+                if (pg.z >= 0) net_emit<K>(tmp, slots.scratch(), valid, out + ((size_t)(valid ? c : 0) * g.n_doy + pg.z) * g.P, g.P, sel);
+                pb = pb1; it = it1; pb1 = pb2; it1 = it2;
+                advance(pb2, it2);
+                continue;
+            }
+        }
         if (d.start == kStartEmpty) {
 #pragma unroll
             for (int e = 0; e < K; e++) run[e] = e < NY ? v[e < NY ? e : 0] : HDP_NET_PAD;
@@ -307,7 +325,7 @@ __device__ __forceinline__ void net_item(int64_t item, const Slots &slots, const
         }
 
         // ---- combine with a stored list; store; look up the requested ranks
-        d.emit_day = emit_day;
+        d.emit_day = irregular ? pg.z : emit_day;
         if (window_of_prefix && emit_day >= 0) d.other = it + 1;
         double *dst = out + ((size_t)(valid ? c : 0) * g.n_doy + max(d.emit_day, 0)) * g.P;
         if (d.other >= 0) {
@@ -344,7 +362,19 @@ k_thr_net(const float *__restrict__ x, int64_t C, uint32_t ld_t,
 {
     extern __shared__ __align__(16) float sm[];
     const SlotsSmem<K> slots{sm + threadIdx.x};
-    net_item<NY, K, M, kPads>(blockIdx.x, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
+    net_item<NY, K, M, kPads, false>(blockIdx.x, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
+}
+
+// The irregular days of one tile (the mirrored year end): one warp per CTA, lists in shared memory, the program of net_plan.
+template <int NY, int K, int M, bool kPads>
+__global__ void __launch_bounds__(32)
+k_thr_net_irr(const float *__restrict__ x, int64_t C, uint32_t ld_t,
+              const int *__restrict__ seq_time, const int *__restrict__ win_day, const int *__restrict__ irr_day, const int *__restrict__ irr_time,
+              const __grid_constant__ NetGeom g, const __grid_constant__ NetSel sel, double *__restrict__ out, const __grid_constant__ NetHandOver hand)
+{
+    extern __shared__ __align__(16) float sm[];
+    const SlotsSmem<K> slots{sm + threadIdx.x};
+    net_item<NY, K, M, kPads, true>(blockIdx.x, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
 }
 
 // The same items on persistent CTAs of 4, 8 or 12 warps (one CTA per SM) that keep most suffix lists in TENSOR MEMORY: twice the
@@ -374,13 +404,13 @@ k_thr_net_tm(const float *__restrict__ x, int64_t C, uint32_t ld_t,
     slots.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * g.tm_cols);
     slots.n_tm = g.tm_lists;
     slots.slot_f = g.M == 3 ? g.s : -1;
-    const unsigned long long n_items = (unsigned long long)(g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0));
+    const unsigned long long n_items = (unsigned long long)(g.n_tiles * g.n_chunks);
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(next_item, 1ULL);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        net_item<NY, K, M, kPads>((int64_t)item, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
+        net_item<NY, K, M, kPads, false>((int64_t)item, slots, x, C, ld_t, seq_time, win_day, irr_day, irr_time, g, sel, out, hand);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -472,7 +502,7 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
     // day d is regular if its window is exactly the sequence rows [d, d + W)
     pl.win_day.assign((size_t)g.n_steps * g.s, -1);
     pl.irr_day.clear(); pl.irr_time.clear();
-    std::vector<int> want(W), have(W);
+    std::vector<int> want(W), have(W), irr;
     for (int d = 0; d < n_doy; d++) {
         bool regular = d < g.n_win;
         if (regular) {
@@ -480,15 +510,75 @@ void net_plan(const int32_t *time_index, const int32_t *win_rows, int64_t T_b, i
             std::sort(want.begin(), want.end()); std::sort(have.begin(), have.end());
             regular = want == have;
         }
-        if (regular) { pl.win_day[d] = d; continue; }
-        pl.irr_day.push_back(d);
-        for (int j = 0; j < W; j++)
-            for (int y = 0; y < g.NY; y++) pl.irr_time.push_back(time_of(win_rows[(size_t)d * W + j], y));
+        if (regular) pl.win_day[d] = d; else irr.push_back(d);
     }
-    g.n_irr = (int)pl.irr_day.size();
+    g.n_irr = (int)irr.size();
     if (g.n_irr * 4 > n_doy) return;                                             // mostly irregular tables: not this kernel
+
+    // The irregular days' program (k_thr_net_irr runs it, one warp per tile).  A step orders one row and merges it into the running
+    // list; flags, slots and the day to emit as documented at NetPlan::irr_day.
+    auto step = [&](int row, int flags, int other, int store_run, int emit_day) {
+        pl.irr_day.push_back(flags);
+        pl.irr_day.push_back((other + 1) | ((store_run + 1) << 8));
+        pl.irr_day.push_back(emit_day);
+        pl.irr_day.push_back(0);
+        for (int y = 0; y < g.NY; y++) pl.irr_time.push_back(time_of(row, y));
+    };
+    // (a) The reference's mirrored year end (hdp/threshold.py:45-47): day d >= n_doy - r pools rows [d - r, n_doy), rows
+    // [2 n_doy - d - r, n_doy) a second time, and row 0.  Both runs are SUFFIXES of the year, so one chain down from the last row
+    // yields them all: the short suffixes (second runs) are stored, row 0 joins the chain once they are, and every further row
+    // finishes one day: 2 r + 2 row steps instead of r W.
+    const int avail = g.M == 3 ? g.s : g.s - 1;                                  // slots besides the scratch slot 0
+    bool mirrored = g.n_irr == r && r >= 1 && r - 1 <= avail + 1;
+    for (int i = 0; mirrored && i < g.n_irr; i++) {
+        const int d = irr[i];
+        mirrored = d == n_doy - r + i;
+        std::vector<int> w2;
+        for (int j = d - r; j < n_doy; j++) w2.push_back(j);
+        for (int j = 2 * n_doy - d - r; j < n_doy; j++) w2.push_back(j);
+        w2.push_back(0);
+        if ((int)w2.size() != W) { mirrored = false; break; }
+        for (int j = 0; j < W; j++) have[j] = win_rows[(size_t)d * W + j];
+        std::sort(w2.begin(), w2.end()); std::sort(have.begin(), have.end());
+        mirrored = mirrored && w2 == have;
+    }
+    if (mirrored) {
+        // second runs start at rows n_doy-1 (day n_doy-r+1) .. n_doy-r+1 (day n_doy-1): r - 1 lists; the one-row list of the last row
+        // is redone as a side step when there is one slot too few
+        const bool side = r - 1 > avail;
+        auto slot_of = [&](int j) { return n_doy - j - (side ? 1 : 0); };        // suffix starting at row j -> slot (1 ..)
+        for (int j = n_doy - 1; j >= n_doy - r + 1; j--)
+            step(j, j == n_doy - 1 ? 1 : 0, -1, (side && j == n_doy - 1) ? -1 : slot_of(j), -1);
+        step(n_doy - r, r == 1 ? 1 : 0, -1, -1, -1);                             // (no day starts or ends its second run here)
+        step(0, 0, -1, -1, -1);                                                  // row 0 joins every irregular window
+        for (int j = n_doy - r - 1; j >= n_doy - 2 * r; j--) {                   // first runs: day d = j + r
+            const int d = j + r, j2 = 2 * n_doy - d - r;                         // its second run starts at row j2 (n_doy: none)
+            if (j2 >= n_doy) step(j, 0, -1, -1, d);
+            else if (side && j2 == n_doy - 1) { step(j, 0, -1, -1, -1); step(n_doy - 1, 2, -1, -1, d); }
+            else step(j, 0, slot_of(j2), -1, d);
+        }
+    } else {
+        // (b) any other irregular window: its rows one by one from the window table
+        for (int d : irr)
+            for (int j = 0; j < W; j++) step(win_rows[(size_t)d * W + j], j == 0 ? 1 : 0, -1, -1, j == W - 1 ? d : -1);
+    }
+    g.n_irr_steps = (int)(pl.irr_day.size() / 4);
     net_set_cells(pl, C);
     pl.usable = true;
+}
+
+// The irregular days: one warp per tile behind (independent of) the regular items.
+template <int NY, int K, int M, bool kPads>
+static int net_launch_irr(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out,
+                          const NetHandOver &hand, cudaStream_t st)
+{
+    const NetGeom &g = pl.geo;
+    if (g.n_irr_steps == 0 || g.n_tiles == 0) return HDP_B200_OK;
+    HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net_irr<NY, K, M, kPads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    k_thr_net_irr<NY, K, M, kPads><<<(unsigned)g.n_tiles, 32, g.smem, st>>>(x, C, (uint32_t)(ld_t * sizeof(float)), tb.seq_time, tb.win_day,
+                                                                           tb.irr_day, tb.irr_time, g, pl.sel, out, hand);
+    HDP_LAUNCH_CHECK();
+    return HDP_B200_OK;
 }
 
 template <int NY, int K, int M, bool kPads>
@@ -497,8 +587,8 @@ static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, 
 {
     const NetGeom &g = pl.geo;
     if (allow_tmem && g.tm_warps > 0 && tb.next_item) {
-        const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
-        if (ld_t <= 0 || ld_t >= (1LL << 30)) return HDP_B200_ERR_UNSUPPORTED;
+        const int64_t items = g.n_tiles * g.n_chunks;
+        if (ld_t <= 0 || ld_t >= (1LL << 30) || g.n_tiles > 0x7fffffffLL) return HDP_B200_ERR_UNSUPPORTED;
         int dev = 0, sms = 0;
         HDP_CUDA_TRY(cudaGetDevice(&dev));
         HDP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -509,15 +599,15 @@ static int net_launch_t(const NetPlan &pl, const NetTables &tb, const float *x, 
         k_thr_net_tm<NY, K, M, kPads><<<grid, g.tm_warps * 32, smem, st>>>(x, C, (uint32_t)(ld_t * sizeof(float)), tb.seq_time, tb.win_day,
                                                                           tb.irr_day, tb.irr_time, g, pl.sel, out, hand, tb.next_item);
         HDP_LAUNCH_CHECK();
-        return HDP_B200_OK;
+        return net_launch_irr<NY, K, M, kPads>(pl, tb, x, C, ld_t, out, hand, st);
     }
     HDP_CUDA_TRY(cudaFuncSetAttribute(k_thr_net<NY, K, M, kPads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    const int64_t items = g.n_tiles * g.n_chunks + (g.n_irr ? g.n_tiles : 0);
+    const int64_t items = g.n_tiles * g.n_chunks;
     if (items > 0x7fffffffLL || ld_t <= 0 || ld_t >= (1LL << 30)) return HDP_B200_ERR_UNSUPPORTED;
     k_thr_net<NY, K, M, kPads><<<(unsigned)items, 32, g.smem, st>>>(x, C, (uint32_t)(ld_t * sizeof(float)), tb.seq_time, tb.win_day, tb.irr_day,
                                                                      tb.irr_time, g, pl.sel, out, hand);
     HDP_LAUNCH_CHECK();
-    return HDP_B200_OK;
+    return net_launch_irr<NY, K, M, kPads>(pl, tb, x, C, ld_t, out, hand, st);
 }
 
 int net_launch(const NetPlan &pl, const NetTables &tb, const float *x, int64_t C, int64_t ld_t, double *out, const NetHandOver &hand, cudaStream_t st,

@@ -28,7 +28,8 @@ struct NetGeom {
     int n_seq;                          // rows of the linear row sequence (n_doy + r); row n_seq of seq_time is the all-pad row
     int n_win;                          // windows 0 .. n_win-1 of W consecutive sequence rows; window k belongs to day win_day[k] (or -1)
     int n_steps, steps_per_chunk, n_chunks;
-    int n_irr;                          // days whose window is not a run of W consecutive rows (mirrored year end): row by row
+    int n_irr;                          // days whose window is not a run of W consecutive rows (the mirrored year end)
+    int n_irr_steps;                    // row steps of the program that works them out (irr_day / irr_time): k_thr_net_irr, one warp per tile
     int64_t n_tiles;                    // 32-cell tiles
     size_t smem;                        // k_thr_net: bytes per one-warp CTA
     // k_thr_net_tm (persistent CTAs, suffix lists in tensor memory): warps per CTA (0 = not used), suffix lists per warp kept in
@@ -42,8 +43,10 @@ struct NetPlan {
     NetSel sel{};
     std::vector<int> seq_time;          // [(n_seq + 1) * NY] time index of every sample of every sequence row, -1 = pad
     std::vector<int> win_day;           // [n_steps * s]
-    std::vector<int> irr_day;           // [n_irr]
-    std::vector<int> irr_time;          // [n_irr * W * NY]
+    std::vector<int> irr_day;           // the irregular days' PROGRAM, 4 ints per row step: {flags (1 = the running list starts over, 2 = the
+                                        // row is merged into a COPY of the running list), (other slot + 1) | (slot the running list is
+                                        // stored to + 1) << 8, day to emit or -1, 0}
+    std::vector<int> irr_time;          // [n_irr_steps * NY] time indices of the row of every step
 };
 
 struct NetTables {                      // device copies (workspace)

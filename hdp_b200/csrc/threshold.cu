@@ -1735,7 +1735,7 @@ static ThrLayout carve_thr(void *ws, size_t ws_bytes, int64_t C, int64_t T_b, bo
     L.handed_over = cv.take<uint32_t>(1 + 2 * L.handed_over_count);       // count, flags[blocks], list[blocks]
     L.net.seq_time = cv.take<int>((size_t)(n_doy + W / 2 + 1) * 32);      // k_thr_net: <= 32 samples per row, n_doy + r rows + the pad row
     L.net.win_day = cv.take<int>((size_t)n_doy + W);
-    L.net.irr_day = cv.take<int>((size_t)n_doy);
+    L.net.irr_day = cv.take<int>((size_t)(n_doy / 4 + 1) * W * 4);        // the irregular days' program: <= W steps per day, 4 ints each
     L.net.irr_time = cv.take<int>((size_t)(n_doy / 4 + 1) * W * 32);      // at most a quarter of the days are irregular (net_plan)
     L.net.next_item = cv.take<unsigned long long>(1);
     L.total = cv.off;

@@ -7,6 +7,8 @@ These are the two seams of the reference that the CUDA library replaces:
 * :func:`metrics_array`     <- ``compute_heatwave_metrics`` + the percentile x definition sweep
   (reference hdp/metric.py:304-369)
 * :func:`hot_days_array`    <- ``indicate_hot_days`` (reference hdp/metric.py:280-301)
+* :func:`index_heatwaves_array`, :func:`season_metrics_array` <- ``index_heatwaves`` and ``heatwave_frequency`` / ``number`` /
+  ``duration`` / ``average`` (reference hdp/metric.py:11-172), the building blocks the hot path never materialises
 
 plus ``*_host`` variants that take NumPy (host) arrays and run the chunked copy/compute pipeline of
 the library.  PyTorch is used only for device allocations and the current stream.  All compute happens
@@ -184,6 +186,48 @@ def hot_days_array(measure, thresholds, doy_map):
         rc = L.hdp_b200_hot_days(measure.data_ptr(), C, T, ld_t, ld_c, thresholds.data_ptr(), n_doy, P, _hp(dm),
                                  out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "hdp_b200_hot_days")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the building blocks of path 2 under the reference's names (reference hdp/metric.py:11-172), csrc/seams.cu
+# ----------------------------------------------------------------------------------------------
+
+def index_heatwaves_array(hot, defs):
+    """``index_heatwaves`` (reference hdp/metric.py:11-60) for S series x D definitions: ``hot`` bool / uint8 CUDA tensor
+    ``[S, T]`` (non-zero = hot day), ``defs`` ``[D, 3]`` -> int64 ``[S, D, T]`` heatwave ids (0 = no heatwave)."""
+    torch = _torch()
+    if not (isinstance(hot, torch.Tensor) and hot.is_cuda and hot.dim() == 2 and hot.dtype in (torch.uint8, torch.bool)):
+        raise TypeError("hot must be a 2-D bool / uint8 CUDA tensor [S, T]")
+    hot = hot.contiguous().view(torch.uint8)
+    df = _i32(defs).reshape(-1, 3)
+    S, T = hot.shape
+    D = int(df.shape[0])
+    out = torch.empty((S, D, T), dtype=torch.int64, device=hot.device)
+    with torch.cuda.device(hot.device):
+        rc = _lib.lib().hdp_b200_index_heatwaves(hot.data_ptr(), S, T, _hp(df), D, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_index_heatwaves")
+    return out
+
+
+def season_metrics_array(hw, season_ranges, want=METRIC_NAMES):
+    """``heatwave_frequency`` / ``number`` / ``duration`` / ``average`` (reference hdp/metric.py:63-172) of S id series: ``hw`` int64
+    CUDA tensor ``[S, T]`` (ANY ids), ``season_ranges`` ``[Y, 2]`` (Python slice semantics) -> dict of the metrics named in
+    ``want``: HWF, HWN, HWD int64 ``[S, Y]``, HWA float64 ``[S, Y]`` (before the truncation of compute_heatwave_metrics)."""
+    torch = _torch()
+    if not (isinstance(hw, torch.Tensor) and hw.is_cuda and hw.dim() == 2 and hw.dtype == torch.int64):
+        raise TypeError("hw must be a 2-D int64 CUDA tensor [S, T]")
+    hw = hw.contiguous()
+    rng = np.ascontiguousarray(season_ranges, dtype=np.int64).reshape(-1, 2)
+    S, T = hw.shape
+    Y = int(rng.shape[0])
+    d_rng = torch.as_tensor(rng).to(hw.device)
+    out = {name: torch.empty((S, Y), dtype=torch.float64 if name == "HWA" else torch.int64, device=hw.device) for name in want}
+    ptr = lambda name: out[name].data_ptr() if name in out else None
+    with torch.cuda.device(hw.device):
+        rc = _lib.lib().hdp_b200_season_metrics(hw.data_ptr(), S, T, d_rng.data_ptr(), Y, ptr("HWF"), ptr("HWN"), ptr("HWD"), ptr("HWA"),
+                                                torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "hdp_b200_season_metrics")
     return out
 
 
@@ -408,7 +452,7 @@ def launch_count() -> int:
 
 
 KERNEL_NAMES = {1: "normalize", 2: "k_thr_generic", 3: "k_hot_words", 4: "k_scan", 5: "k_unpack_mask",
-                6: "k_thr_seg", 7: "k_thr_ranked", 8: "k_measure", 9: "k_thr_cand", 10: "k_thr_net"}
+                6: "k_thr_seg", 7: "k_thr_ranked", 8: "k_measure", 9: "k_thr_cand", 10: "k_thr_net", 11: "k_seam"}
 
 
 def timing_enable(on: bool) -> None:

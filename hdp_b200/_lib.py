@@ -39,6 +39,8 @@ SIGNATURES = {
     "hdp_b200_timing_enable": (None, [_int]),
     "hdp_b200_timing_read": (_int, [_p, _p, _int]),
     "hdp_b200_hot_days": (_int, [_p, _i64, _i64, _i64, _i64, _p, _int, _int, _p, _p, _p, _sz, _p]),
+    "hdp_b200_index_heatwaves": (_int, [_p, _i64, _i64, _p, _int, _p, _p]),
+    "hdp_b200_season_metrics": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _p, _p]),
 }
 
 _LIB: Optional[ctypes.CDLL] = None
@@ -67,7 +69,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)          # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
-        if L.hdp_b200_abi_version() != 3:
+        if L.hdp_b200_abi_version() != 4:
             raise RuntimeError("libhdp_b200.so ABI version mismatch; rebuild with `python -m hdp_b200.build --force`")
         _LIB = L
     return _LIB

@@ -78,6 +78,12 @@ def heat_index(temp, rel_humid) -> np.ndarray:
     return np.where(hi > 80, full, hi).astype(np.float32)
 
 
+def heat_index_map_wrapper(ds):
+    """hdp/measure.py:97-108: ``heat_index`` over the ``temp`` (degF) and ``rh`` (%) variables of a dataset, float32."""
+    temp = ds["temp"]
+    return _with_values(temp, heat_index(xr.values_of(temp).astype(np.float32), xr.values_of(ds["rh"]).astype(np.float32)))
+
+
 def apply_heat_index(temp, rh):
     """hdp/measure.py:111-133"""
     assert temp.attrs["units"] == "degF"

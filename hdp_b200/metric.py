@@ -24,6 +24,79 @@ METRIC_ATTRS = {          # metric.py:473-492
 }
 
 
+# ----------------------------------------------------------------------------------------------
+# The building blocks under the reference's names (its unit tests import exactly these: hdp/tests/test_index_heatwaves.py,
+# test_heatwave_{frequency,number,duration,average}.py).  Host arrays in and out like the Numba functions, computed on the GPU
+# (csrc/seams.cu); compute_group_metrics does not go through them - its fused kernels never build the id series.
+# ----------------------------------------------------------------------------------------------
+
+def _to_device(a: np.ndarray):
+    import torch
+    _core._torch()                                                  # raises without a CUDA device: there is no CPU path
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def index_heatwaves(hot_days_ts, min_duration: int, max_break: int, max_subs: int) -> np.ndarray:
+    """metric.py:11-60: bool / 0-1 series of hot days -> int64 series of heatwave ids (0 = no heatwave)."""
+    hot = np.asarray(hot_days_ts)
+    if hot.ndim != 1:
+        raise ValueError("hot_days_ts must be one-dimensional")
+    hot = (hot != 0).astype(np.uint8)                               # `if hot_days_ts[i]`, metric.py:29
+    out = _core.index_heatwaves_array(_to_device(hot[None, :]), [[min_duration, max_break, max_subs]])
+    return out[0, 0].cpu().numpy()
+
+
+def _season_metric(hw_ts, season_ranges, name: str) -> np.ndarray:
+    hw = np.asarray(hw_ts)
+    if hw.ndim != 1:
+        raise ValueError("hw_ts must be one-dimensional")
+    rng = np.asarray(season_ranges, dtype=np.int64).reshape(-1, 2)
+    if name in ("HWD", "HWA") and rng.shape[0]:
+        # a season whose slice hw_ts[a:b] is empty: the reference's np.max / np.mean of nothing raise
+        T = hw.size
+        lo = np.clip(np.where(rng[:, 0] < 0, rng[:, 0] + T, rng[:, 0]), 0, T)
+        hi = np.clip(np.where(rng[:, 1] < 0, rng[:, 1] + T, rng[:, 1]), 0, T)
+        if np.any(hi <= lo):
+            if name == "HWD":
+                raise ValueError("zero-size array to reduction operation maximum which has no identity")
+            raise ZeroDivisionError("division by zero")
+    out = _core.season_metrics_array(_to_device(hw.astype(np.int64)[None, :]), rng, want=(name,))
+    return out[name][0].cpu().numpy()
+
+
+def heatwave_number(hw_ts, season_ranges) -> np.ndarray:
+    """metric.py:63-82 (HWN): distinct non-zero ids in every season slice, int64[Y]."""
+    return _season_metric(hw_ts, season_ranges, "HWN")
+
+
+def heatwave_frequency(hw_ts, season_ranges) -> np.ndarray:
+    """metric.py:85-102 (HWF): days with id > 0 in every season slice, int64[Y]."""
+    return _season_metric(hw_ts, season_ranges, "HWF")
+
+
+def heatwave_duration(hw_ts, season_ranges) -> np.ndarray:
+    """metric.py:105-137 (HWD): most days carrying one id inside every season slice, int64[Y]."""
+    return _season_metric(hw_ts, season_ranges, "HWD")
+
+
+def heatwave_average(hw_ts, season_ranges) -> np.ndarray:
+    """metric.py:140-172 (HWA): mean number of days per id inside every season slice, float64[Y]."""
+    return _season_metric(hw_ts, season_ranges, "HWA")
+
+
+def indicate_hot_days(measure, threshold, doy_map) -> np.ndarray:
+    """metric.py:280-301: ``measure[t] > threshold[doy_map[t]]`` (float32 against float64, compared in double; NaN -> False)."""
+    m = np.asarray(measure)
+    if m.ndim != 1:
+        raise ValueError("measure must be one-dimensional")
+    m32 = m.astype(np.float32)
+    if m.dtype != np.float32 and not np.array_equal(m32.astype(np.float64), m.astype(np.float64), equal_nan=True):
+        raise TypeError("measure must be float32 (or exactly representable in it): the device path compares float32 samples")
+    thr = np.ascontiguousarray(threshold, dtype=np.float64).reshape(1, -1, 1)
+    out = _core.hot_days_array(_to_device(m32.reshape(-1, 1)), _to_device(thr), np.asarray(doy_map))
+    return out[0, :, 0].cpu().numpy().astype(bool)
+
+
 def build_doy_map(times) -> np.ndarray:
     """metric.py:265-277"""
     axis = times if isinstance(times, _tables.TimeAxis) else _tables.TimeAxis.from_datetimes(list(times))
@@ -90,6 +163,43 @@ def _widen_int64(a: np.ndarray) -> np.ndarray:
     return out
 
 
+def _metric_sweep(measure, threshold, hw_definitions, time_axis, doy_map=None):
+    """The percentile x definition x cell sweep of compute_heatwave_metrics_wrapper (metric.py:344-369) as ONE library call:
+    -> (uint16 [4, P, D, Y, C], season tables, cell dims, cell shape, P, D)."""
+    st = _tables.hemisphere_ranges(time_axis)                       # compute_hemisphere_ranges, :410
+    if doy_map is None:
+        doy_map = _tables.doy_map(time_axis.dayofyr)                # build_doy_map, :413
+    x, cell_dims, cell_shape = _layout.to_time_cells(xr.values_of(measure), tuple(measure.dims), require_float32=True)
+    south = _tables.is_south(_layout.cell_latitudes(xr.coord_values(measure, "lat"), cell_dims, cell_shape))
+
+    # thresholds [<cells in the measure's order>, doy, percentile] -> [C, n_doy, P]; exact coordinate join like apply_ufunc
+    thr_dims = tuple(threshold.dims)
+    want = [*cell_dims, "doy", "percentile"]
+    if sorted(thr_dims) != sorted(want):
+        raise ValueError(f"threshold dims {thr_dims} do not match measure dims {tuple(measure.dims)}")
+    for d in cell_dims:
+        if not np.array_equal(np.asarray(xr.coord_values(threshold, d)), np.asarray(xr.coord_values(measure, d))):
+            raise ValueError(f"cannot align measure and threshold exactly along '{d}'")
+    thr_vals = np.transpose(xr.values_of(threshold), [thr_dims.index(d) for d in want]).astype(np.float64, copy=False)
+    n_doy, P = thr_vals.shape[-2], thr_vals.shape[-1]
+    thr_cdp = np.ascontiguousarray(thr_vals).reshape(-1, n_doy, P)
+
+    defs = np.asarray(hw_definitions, dtype=np.int64).reshape(-1, 3)
+    out = _core.metrics_host(x, thr_cdp, doy_map, defs, st.north, st.south, south)     # uint16 [4, P, D, Y, C]
+    return out, st, cell_dims, cell_shape, P, defs.shape[0]
+
+
+def compute_heatwave_metrics_wrapper(measure, threshold, doy_map, hw_definitions):
+    """metric.py:344-369: the four metrics of every cell for every percentile and definition as one int64 array with dims
+    ``(percentile, definition, <cells>, metric, year)``; ``metric`` = HWF, HWN, HWD, HWA in this order (:336-340)."""
+    dm = None if doy_map is None else np.asarray(getattr(doy_map, "values", doy_map))
+    out, st, cell_dims, cell_shape, P, D = _metric_sweep(measure, threshold, hw_definitions, time_axis_of(measure), dm)
+    data = out.astype(np.int64).transpose(1, 2, 4, 0, 3).reshape(P, D, *cell_shape, 4, st.n_years)
+    coords = {"definition": [f"{hw_def[0]}-{hw_def[1]}-{hw_def[2]}" for hw_def in hw_definitions],      # :347-350
+              "percentile": np.asarray(xr.coord_values(threshold, "percentile"))}
+    return xr.DataArray(data, dims=["percentile", "definition", *cell_dims, "metric", "year"], coords=coords)
+
+
 def compute_individual_metrics(measure, threshold, hw_definitions: list, include_threshold: bool = True, check_variables: bool = True):
     """metric.py:372-506."""
     time_axis = time_axis_of(measure)
@@ -109,26 +219,8 @@ def compute_individual_metrics(measure, threshold, hw_definitions: list, include
             if entry != '':
                 combined_history += (f"(Threshold) {entry}\n")
 
-    st = _tables.hemisphere_ranges(time_axis)                       # compute_hemisphere_ranges, :410
-    doy_map = _tables.doy_map(time_axis.dayofyr)                    # build_doy_map, :413
-    x, cell_dims, cell_shape = _layout.to_time_cells(xr.values_of(measure), tuple(measure.dims), require_float32=True)
-    south = _tables.is_south(_layout.cell_latitudes(xr.coord_values(measure, "lat"), cell_dims, cell_shape))
-
-    # thresholds [<cells in the measure's order>, doy, percentile] -> [C, n_doy, P]; exact coordinate join like apply_ufunc
-    thr_dims = tuple(threshold.dims)
-    want = [*cell_dims, "doy", "percentile"]
-    if sorted(thr_dims) != sorted(want):
-        raise ValueError(f"threshold dims {thr_dims} do not match measure dims {tuple(measure.dims)}")
-    for d in cell_dims:
-        if not np.array_equal(np.asarray(xr.coord_values(threshold, d)), np.asarray(xr.coord_values(measure, d))):
-            raise ValueError(f"cannot align measure and threshold exactly along '{d}'")
-    thr_vals = np.transpose(xr.values_of(threshold), [thr_dims.index(d) for d in want]).astype(np.float64, copy=False)
-    n_doy, P = thr_vals.shape[-2], thr_vals.shape[-1]
-    thr_cdp = np.ascontiguousarray(thr_vals).reshape(-1, n_doy, P)
-
-    defs = np.asarray(hw_definitions, dtype=np.int64).reshape(-1, 3)
-    out = _core.metrics_host(x, thr_cdp, doy_map, defs, st.north, st.south, south)     # uint16 [4, P, D, Y, C]
-    D, Y = defs.shape[0], st.n_years
+    out, st, cell_dims, cell_shape, P, D = _metric_sweep(measure, threshold, hw_definitions, time_axis)
+    Y = st.n_years
 
     coords = dict(xr.non_time_coords(measure))
     coords["definition"] = [f"{hw_def[0]}-{hw_def[1]}-{hw_def[2]}" for hw_def in hw_definitions]   # :432
@@ -175,3 +267,40 @@ def compute_group_metrics(measures, thresholds, hw_definitions: list, include_th
     aggr_ds.attrs["variable_naming_desc"] = "(heat measure).(threshold used).(heatwave metric)"
     aggr_ds.attrs["variable_naming_delimeter"] = "."
     return aggr_ds
+
+
+def compute_metrics_io(output_path: str, measure_path: str, measure_var: str, threshold_path: str, hw_definitions: list,
+                       include_threshold: bool = False, override_threshold_var: str = None, overwrite: bool = False) -> None:
+    """hdp/metric.py:526-590: metrics from netCDF files / zarr stores, written back to disk.  The reference's wrapper does not run
+    as shipped (``overwrite`` and ``makedirs`` are undefined, ``threshold_var`` is unset when an override is given); this one
+    does what it sets out to do (``overwrite`` is the argument the reference forgot to declare).  netCDF / zarr need xarray;
+    without it (this image) use :func:`hdp_b200.io.compute_metrics_io`, the same flow on memory-mapped ``.npy`` files."""
+    import os
+    from pathlib import Path
+    output_path, measure_path, threshold_path = Path(output_path), Path(measure_path), Path(threshold_path)
+    check_variables = True
+    threshold_var = override_threshold_var
+    if override_threshold_var is None:                              # :562-564
+        threshold_var = f"threshold_{measure_var}"
+        check_variables = False
+    if output_path.exists() and not overwrite:
+        raise FileExistsError(f"Overwrite parameter set to False and file exists at '{output_path}'.")
+    if not output_path.parent.exists():
+        if overwrite:
+            os.makedirs(output_path.parent, exist_ok=True)
+        else:
+            raise FileExistsError(f"Overwrite parameter set to False and directory '{output_path.parent}' does not exist.")
+    if output_path.suffix not in [".zarr", ".nc"]:
+        raise ValueError(f"File type '{output_path.suffix}' from '{output_path}' not supported.")
+    if not xr.HAVE_XARRAY:
+        raise RuntimeError("reading netCDF / zarr needs xarray; hdp_b200.io.compute_metrics_io streams .npy files without it")
+    import xarray                                                   # pragma: no cover - no xarray in the build image
+
+    def _open(path, var):                                           # pragma: no cover
+        return (xarray.open_zarr(path) if path.suffix == ".zarr" and path.is_dir() else xarray.open_dataset(path))[var]
+    metric_ds = compute_individual_metrics(_open(measure_path, measure_var), _open(threshold_path, threshold_var), hw_definitions,
+                                           include_threshold=include_threshold, check_variables=check_variables)   # pragma: no cover
+    if output_path.suffix == ".zarr":                               # pragma: no cover
+        metric_ds.to_zarr(output_path, mode="w" if overwrite else "w-")
+    else:                                                           # pragma: no cover
+        metric_ds.to_netcdf(output_path)

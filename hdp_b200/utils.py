@@ -36,6 +36,17 @@ def add_history(ds, msg):
     return ds
 
 
+def get_func_description(func) -> str:
+    """hdp/utils.py:27-36: the prose of a docstring up to its first ``:param`` line, on one line."""
+    words = []
+    for line in func.__doc__.split("\n"):
+        if ":param" in line:
+            break
+        if line.strip():
+            words.append(line.strip() + " ")
+    return "".join(words)
+
+
 def time_axis_of(obj) -> TimeAxis:
     """Integer calendar fields of the ``time`` coordinate (cftime objects with xarray, a TimeAxis with the stand-in)."""
     t = xr.coord_values(obj, "time")

@@ -12,7 +12,9 @@
  *                                   (indicate_hot_days :280-301, index_heatwaves :11-60,
  *                                    heatwave_frequency/number/duration/average :63-172)
  *                                   + compute_heatwave_metrics_wrapper     hdp/metric.py:344-369
- *   hdp_b200_hot_days     replaces  indicate_hot_days                     hdp/metric.py:280-301   (parity checks)
+ *   hdp_b200_hot_days     replaces  indicate_hot_days                     hdp/metric.py:280-301
+ *   hdp_b200_index_heatwaves   replaces  index_heatwaves                  hdp/metric.py:11-60     (the building blocks under
+ *   hdp_b200_season_metrics    replaces  heatwave_frequency / number / duration / average  hdp/metric.py:63-172   their own names)
  *   *_host variants       the same calls with HOST buffers (cell chunks pipelined H2D -> kernels -> D2H on three streams).
  *
  * Conventions
@@ -40,7 +42,7 @@
 extern "C" {
 #endif
 
-#define HDP_B200_ABI_VERSION 3
+#define HDP_B200_ABI_VERSION 4
 
 #define HDP_B200_OK                 0
 #define HDP_B200_ERR_INVALID       (-1)  /* null pointer, negative size, quantile outside [0,1] or NaN, bad table entry */
@@ -167,6 +169,26 @@ int hdp_b200_hot_days(const float *d_measure, int64_t C, int64_t T, int64_t ld_t
                       void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * The building blocks of path 2 under the reference's own names.  hdp_b200_metrics never materialises what they exchange
+ * (the per-day heatwave id series), but the reference exposes them and its unit tests call them directly
+ * (hdp/tests/test_index_heatwaves.py, test_heatwave_{frequency,number,duration,average}.py); these two entry points give
+ * the Python mirror (hdp_b200.metric.index_heatwaves, heatwave_*) a device implementation with the reference's semantics
+ * for ARBITRARY inputs.  S independent series, each contiguous in time.
+ *
+ *   hdp_b200_index_heatwaves   d_hot u8 [S, T] (non-zero = hot day, metric.py:28-30), h_defs i32 [D, 3] as for
+ *                              hdp_b200_metrics  ->  d_hw i64 [S, D, T] heatwave ids, 0 = no heatwave (metric.py:11-60)
+ *   hdp_b200_season_metrics    d_hw i64 [S, T] ANY id series, d_seasons i64 [Y, 2] [start, end) with Python slice
+ *                              semantics (DEVICE table: Y is unbounded)  ->  d_hwf, d_hwn, d_hwd i64 [S, Y], d_hwa f64 [S, Y]
+ *                              (each may be NULL): days with id > 0 (metric.py:85-102), distinct non-zero ids (:63-82),
+ *                              longest / mean number of days per id with the reference's handling of np.unique - the
+ *                              smallest distinct value is dropped when there are several (:105-172).  An empty slice
+ *                              yields 0 (the reference raises in duration / average: the Python mirror does too).
+ * ------------------------------------------------------------------------------------------------- */
+int hdp_b200_index_heatwaves(const uint8_t *d_hot, int64_t S, int64_t T, const int32_t *h_defs, int D, int64_t *d_hw, void *stream);
+int hdp_b200_season_metrics(const int64_t *d_hw, int64_t S, int64_t T, const int64_t *d_seasons, int Y,
+                            int64_t *d_hwf, int64_t *d_hwn, int64_t *d_hwd, double *d_hwa, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Elementwise pre-pass of hdp.measure on the device ("next" row of the scope table; format_standard_measures itself
  * stays host Python).   reference: hdp/measure.py:10-94, 183-194.  All arrays are dense f32 of n elements; in-place
  * (d_out == d_temp) is allowed.  Results are bit-identical to the reference's Numba / NumPy float32 arithmetic.
@@ -201,6 +223,8 @@ int64_t hdp_b200_launch_count(void);
 #define HDP_B200_KERNEL_THR_RANKED   7   /* k_thr_ranked */
 #define HDP_B200_KERNEL_MEASURE      8   /* k_measure */
 #define HDP_B200_KERNEL_THR_CAND     9   /* k_thr_cand */
+#define HDP_B200_KERNEL_THR_NET     10   /* k_thr_net / k_thr_net_tm / k_thr_net_irr */
+#define HDP_B200_KERNEL_SEAM        11   /* k_index_heatwaves, k_season_metrics */
 void hdp_b200_timing_enable(int on);
 int  hdp_b200_timing_read(int *ids, float *ms, int cap);
 

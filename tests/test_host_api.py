@@ -110,6 +110,66 @@ def test_mini_merge_exact_join():
         xr.mini_merge([a, c])
 
 
+def test_mirror_exports_every_function_of_the_reference_modules():
+    """Every public function of hdp/{threshold,metric,measure,utils}.py exists under the same name (reference line in brackets)."""
+    from hdp_b200 import metric, threshold
+    surface = {
+        threshold: ["datetimes_to_windows", "compute_percentiles", "compute_percentiles_wrapper", "compute_threshold",       # :12 :59 :81 :96
+                    "compute_thresholds", "compute_threshold_io"],                                                          # :207 :232
+        metric: ["index_heatwaves", "heatwave_number", "heatwave_frequency", "heatwave_duration", "heatwave_average",        # :12 :64 :86 :106 :141
+                 "get_range_indices", "compute_hemisphere_ranges", "build_doy_map", "indicate_hot_days",                     # :175 :212 :265 :281
+                 "compute_heatwave_metrics", "compute_heatwave_metrics_wrapper", "compute_individual_metrics",               # :305 :344 :372
+                 "compute_group_metrics", "compute_metrics_io"],                                                            # :509 :526
+        measure: ["kelvin_to_celsius", "fahrenheit_to_celsius", "celsius_to_fahrenheit", "heat_index", "heat_index_map_wrapper",   # :10 :27 :44 :62 :97
+                  "apply_heat_index", "convert_temp_units", "format_standard_measures"],                                    # :111 :136 :152
+        utils: ["get_time_stamp", "add_history", "get_version", "get_func_description", "generate_test_warming_dataarray",   # :10 :14 :23 :27 :39
+                "generate_test_rh_dataarray", "generate_test_control_dataarray"],                                           # :45 :53
+    }
+    for module, names in surface.items():
+        for name in names:
+            assert callable(getattr(module, name, None)), f"{module.__name__}.{name}"
+
+
+def test_io_wrappers_keep_the_reference_errors(tmp_path):
+    """hdp/threshold.py:264-277, hdp/metric.py:566-576: FileExistsError / ValueError before anything is read."""
+    from hdp_b200 import metric, threshold
+    existing = tmp_path / "there.nc"
+    existing.write_bytes(b"x")
+    with pytest.raises(FileExistsError):
+        threshold.compute_threshold_io("in.nc", "tas", str(existing), [0.9])
+    with pytest.raises(FileExistsError):
+        threshold.compute_threshold_io("in.nc", "tas", str(tmp_path / "missing_dir" / "out.nc"), [0.9])
+    with pytest.raises(ValueError):
+        threshold.compute_threshold_io("in.nc", "tas", str(tmp_path / "out.txt"), [0.9])
+    with pytest.raises(FileExistsError):
+        metric.compute_metrics_io(str(existing), "m.nc", "tas", "t.nc", [[3, 0, 0]])
+    with pytest.raises(ValueError):
+        metric.compute_metrics_io(str(tmp_path / "out.csv"), "m.nc", "tas", "t.nc", [[3, 0, 0]])
+    if not xr.HAVE_XARRAY:
+        with pytest.raises(RuntimeError, match="hdp_b200.io"):
+            threshold.compute_threshold_io("in.nc", "tas", str(tmp_path / "out.nc"), [0.9])
+
+
+def test_get_func_description_and_heat_index_map_wrapper():
+    def documented():
+        """First line.
+
+        Second line,
+        continued.
+
+        :param x: not part of the description
+        """
+    assert utils.get_func_description(documented) == "First line. Second line, continued. "       # hdp/utils.py:27-36
+    g = np.load(os.path.join(GOLDEN, "measure.npz"))
+    t, rh = np.asarray(g["t"]).ravel()[:600].reshape(20, 30), np.asarray(g["rh"]).ravel()[:600].reshape(20, 30)
+    coords = {"lat": np.arange(20.0), "lon": np.arange(30.0)}
+    ds = xr.Dataset({"temp": xr.DataArray(t.astype(np.float64), dims=["lat", "lon"], coords=coords, name="temp", attrs={"units": "degF"}),
+                     "rh": xr.DataArray(rh, dims=["lat", "lon"], coords=coords, name="rh", attrs={"units": "%"})})
+    hi = measure.heat_index_map_wrapper(ds)                                                        # hdp/measure.py:97-108
+    assert tuple(hi.dims) == ("lat", "lon") and hi.dtype == np.float32
+    assert np.array_equal(xr.values_of(hi).ravel().view(np.uint32), np.asarray(g["hi"]).ravel()[:600].view(np.uint32))
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_reference_workflow_through_drop_in_api():

@@ -19,10 +19,10 @@ def ref():
     from oracle import build as obuild, ref_numba
     if obuild.build_ref() is None or not ref_numba.available():
         pytest.skip("no reference tree and no earlier install")
-    thr_mod, met_mod, _ = ref_numba.load()
+    thr_mod, met_mod, mea_mod = ref_numba.load()
 
     class Ref:
-        threshold, metric = thr_mod, met_mod
+        threshold, metric, measure = thr_mod, met_mod, mea_mod
 
         @staticmethod
         def dates(axis):
@@ -114,3 +114,19 @@ def test_table_builders_fuzz_vs_reference(ref, calendar):
         assert np.array_equal(tb.doy_map(ax.dayofyr), ref.metric.build_doy_map(dates))
         for s, e in (((5, 1), (10, 1)), ((11, 1), (4, 1))):
             assert np.array_equal(tb.range_indices(ax, s, e), ref.metric.get_range_indices(dates, s, e)), (start, s, e)
+
+
+def test_heat_index_fuzz_vs_reference(ref):
+    """The NWS heat index ufunc (hdp/measure.py:61-94, float64 inside Numba, float32 out) over every branch of the regression:
+    the host mirror is bit-identical on fresh random inputs (the device pre-pass is checked against the same function's golden)."""
+    from hdp_b200 import measure
+    rng = np.random.default_rng(5)
+    t = np.concatenate([rng.uniform(-20, 130, 20000), rng.uniform(79, 113, 20000), rng.uniform(79.5, 87.5, 10000)]).astype(np.float32)
+    rh = np.concatenate([rng.uniform(0, 100, 20000), rng.uniform(0, 14, 20000), rng.uniform(84, 100, 10000)]).astype(np.float32)
+    t[:5] = [80.0, 87.0, 112.0, np.nan, 95.0]
+    rh[:5] = [13.0, 85.0, 12.99, 50.0, np.nan]
+    want = ref.measure.heat_index(t, rh)
+    got = measure.heat_index(t, rh)
+    assert got.dtype == np.float32 and want.dtype == np.float32
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
